@@ -1,0 +1,107 @@
+/*
+ * s3prl_b200 — C ABI of the Blackwell (sm_100a) upstream feature-extraction hot path.
+ *
+ * Plain pointers and sizes only (no torch types). Every entry point returns 0 on success and a
+ * non-zero status otherwise; s3b_last_error() returns a thread-local message for the last failure.
+ * The Python binding a reference maintainer would add is the ctypes stub in INTEGRATION.md
+ * (ours: s3prl_b200/lib.py). Citations are to the reference tree s3prl/s3prl @ 0.4.18.
+ */
+#ifndef S3PRL_B200_H_
+#define S3PRL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct s3b_model s3b_model;
+
+/* Architecture of one wav2vec2 / HuBERT / WavLM upstream.
+ * Mirrors the fields of HubertConfig (s3prl/upstream/hubert/hubert_model.py:76-278),
+ * Wav2Vec2Config (s3prl/upstream/wav2vec2/wav2vec2_model.py:2103-2350) and
+ * WavLMConfig (s3prl/upstream/wavlm/WavLM.py:162-245) that the extraction forward reads. */
+typedef struct s3b_config {
+    int32_t family;               /* 0 = hubert, 1 = wav2vec2, 2 = wavlm (selects frame-mask rule, T2 handling) */
+    int32_t extractor_layer_norm; /* 0: extractor_mode "default" (GroupNorm after conv 0); 1: "layer_norm" */
+    int32_t conv_bias;            /* conv_bias */
+    int32_t layer_norm_first;     /* pre-LN transformer (large_ll60k, wavlm_large) */
+    int32_t normalize_wav;        /* task_cfg.normalize: per-utterance F.layer_norm of the waveform */
+    int32_t num_layers;           /* encoder_layers */
+    int32_t embed_dim;            /* encoder_embed_dim (multiple of 128) */
+    int32_t ffn_dim;              /* encoder_ffn_embed_dim */
+    int32_t num_heads;            /* encoder_attention_heads; head dim must be 64 */
+    int32_t pos_conv_kernel;      /* conv_pos (128) */
+    int32_t pos_conv_groups;      /* conv_pos_groups (16) */
+    int32_t relative_position;    /* WavLM relative_position_embedding */
+    int32_t num_buckets;          /* WavLM num_buckets (320) */
+    int32_t max_distance;         /* WavLM max_distance (800) */
+    int32_t gru_rel_pos;          /* WavLM gru_rel_pos */
+    int32_t reserved[8];
+} s3b_config;
+
+/* Library / error ------------------------------------------------------------------------------ */
+int s3b_version(void);
+const char* s3b_last_error(void);
+/* number of CUDA devices visible (0 on a GPU-less host; never fails) */
+int s3b_device_count(void);
+
+/* Model lifetime --------------------------------------------------------------------------------
+ * Replaces load_converted_model + HubertModel(...).load_state_dict
+ * (s3prl/upstream/hubert/convert.py:37-56, wav2vec2/convert.py:26-39, wavlm/expert.py:37-44).
+ * Tensors are passed by their reference state-dict key, fp32, host memory, C-contiguous.
+ * Unknown keys (pre-training heads: mask_emb, final_proj, quantizer.*, ...) are ignored.
+ * s3b_model_finalize folds weight_norm of pos_conv, re-lays conv weights for channels-last implicit GEMM,
+ * splits every GEMM weight into bf16 hi/lo, uploads to the current CUDA device. */
+int s3b_model_create(const s3b_config* cfg, s3b_model** out);
+int s3b_model_set_tensor(s3b_model* m, const char* name, const float* data, const int64_t* shape, int32_t ndim);
+int s3b_model_finalize(s3b_model* m);
+void s3b_model_destroy(s3b_model* m);
+
+/* Frame bookkeeping (bit-exact integer rules) ------------------------------------
+ * T = conv-stack output length for a padded batch of max length max_len
+ * (ConvFeatureExtractionModel, wav2vec2_model.py:2857-2934). Returns -1 if max_len is too short. */
+int64_t s3b_num_frames(const s3b_model* m, int64_t max_len);
+/* valid_frames[b] = number of un-padded frames of utterance b inside a batch padded to max_len:
+ * HuBERT/WavLM chunk-all rule (hubert_model.py:454-464, WavLM.py:339-349) or the wav2vec2 conv-length
+ * rule (wav2vec2_model.py:2610-2625,2652-2671). frame t of utterance b is padding iff t >= valid_frames[b]. */
+int s3b_valid_frames(const s3b_model* m, const int64_t* lens, int32_t batch, int64_t max_len, int32_t* valid_frames);
+
+/* The hot path ------------------------------------------------------------------------------------
+ * Replaces UpstreamExpert.forward + hooks (hubert/expert.py:36-72, wav2vec2/expert.py:61-97,
+ * wavlm/expert.py:45-87, interfaces.py:100-131).
+ *  wavs        : host array of `batch` DEVICE pointers to fp32 waveforms (un-padded, any order)
+ *  lens        : host array of `batch` lengths (samples)
+ *  max_len     : padded batch length Lmax (>= max(lens); equal to it for single-GPU use; the global max of
+ *                the un-sharded batch when the batch is sharded across ranks)
+ *  hidden_out  : DEVICE buffer [num_layers+1][batch][T][embed_dim] fp32, T = s3b_num_frames(max_len)
+ *  stream      : cudaStream_t the work is enqueued on (asynchronous with respect to the host) */
+int s3b_forward(s3b_model* m, const float* const* wavs, const int64_t* lens, int32_t batch, int64_t max_len,
+                float* hidden_out, void* stream);
+/* Same, end-to-end from HOST buffers: waveforms are host pointers, hidden_out is a host buffer; the
+ * host<->device copies are part of the call, which returns after the result has landed. */
+int s3b_forward_host(s3b_model* m, const float* const* wavs, const int64_t* lens, int32_t batch, int64_t max_len,
+                     float* hidden_out);
+
+/* Featurizer (s3prl/upstream/interfaces.py:217-248) --------------------------------------------------
+ * out[i] = sum_l w[l] * hs[l][i], hs = [num][n_per_layer] fp32 device, w = device (already softmaxed). */
+int s3b_weighted_sum(const float* hs, int32_t num, int64_t n_per_layer, const float* w, float* out, void* stream);
+/* grad_w[l] = sum_i hs[l][i] * grad_out[i] */
+int s3b_weighted_sum_backward(const float* hs, int32_t num, int64_t n_per_layer, const float* grad_out,
+                              float* grad_w, void* stream);
+
+/* Building blocks exposed for parity tests (device pointers, fp32) -------------------------------------- */
+/* out[M][N] = act(A[M][K] * W[N][K]^T + bias[N]) (+ residual[M][N]); K % 64 == 0, N % 16 == 0 */
+int s3b_linear_f32(const float* a, const float* w, const float* bias, const float* residual, int64_t m, int32_t n,
+                   int32_t k, int32_t gelu, float* out, void* stream);
+/* y = LayerNorm_D(x) (eps 1e-5), optional GELU; D in {512,768,1024,1280} */
+int s3b_layernorm_f32(const float* x, int64_t m, int32_t d, const float* gamma, const float* beta, int32_t gelu,
+                      float* out, void* stream);
+/* softmax(q k^T / 8 + key padding mask) v per (batch, head); q,k,v: [batch][T][heads*64] fp32 */
+int s3b_attention_f32(const float* q, const float* k, const float* v, const int32_t* valid_frames, int32_t batch,
+                      int32_t t, int32_t heads, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S3PRL_B200_H_ */

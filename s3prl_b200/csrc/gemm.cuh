@@ -1,0 +1,65 @@
+// Host-visible description of one error-compensated (bf16 hi/lo, 3-MMA) tcgen05 GEMM launch.
+// One kernel serves every contraction on the hot path: the strided conv stack
+// (conv 1..6 as implicit GEMM on channels-last activations), post_extract_proj, the grouped positional
+// conv (one k-block per tap, time shift expressed in the TMA row coordinate), QKV, out_proj, fc1, fc2.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace s3b {
+
+struct GemmParams {
+    // A operand (activations): bf16 hi / lo, 3-D tensor maps (k, row, batch), box {64, 128, 1}, SWIZZLE_128B
+    CUtensorMap a_hi, a_lo;
+    // B operand (weights, [N][K] K-major): bf16 hi / lo, 3-D tensor maps (k, n, z), box {64, umma_n, 1}
+    CUtensorMap b_hi, b_lo;
+
+    // ---- tiling -------------------------------------------------------------------------------
+    int batches;            // extent of A's 3rd dim that is tiled over
+    int rows_per_batch;     // valid output rows per batch
+    int tiles_m_per_batch;  // ceil(rows_per_batch / 128)
+    int n_tiles;            // output column tiles
+    int umma_n;             // columns per tile (multiple of 16, <= 256)
+    int num_k_blocks;       // k-blocks (of 64 elements) per output tile
+    // k-block kb reads   A box at (a_k_per_ntile*n_tile + (kb % kb_per_row)*64,
+    //                              row0 + (kb / kb_per_row)*a_row_step + a_row_off, batch)
+    //                    B box at (b_k_linear ? kb*64 : (kb % kb_per_row)*64, b_n_tiled ? n_tile*umma_n : 0,
+    //                              b_k_linear ? 0 : kb / kb_per_row + n_tile*b_z_per_ntile)
+    int kb_per_row;
+    int a_row_step;
+    int a_row_off;
+    int a_k_per_ntile;
+    int b_n_tiled;
+    int b_k_linear;
+    int b_z_per_ntile;
+
+    // ---- epilogue: v = acc (+bias[n]) ; gelu? ; (+residual[m][n]) ; row_mask[m] ? 0 -----------------
+    int out_rows_per_batch;  // flat output row m = batch*out_rows_per_batch + row
+    int ldo;                 // leading dimension (elements) of out_f32/out_hi/out_lo/residual
+    const float* bias;
+    const float* residual;
+    const uint8_t* row_mask;
+    int gelu;
+    float* out_f32;
+    __nv_bfloat16* out_hi;
+    __nv_bfloat16* out_lo;
+
+    // ---- epilogue, QKV scatter mode (qkv_mode != 0): columns [0,D) -> q*scale, [D,2D) -> k, [2D,3D) -> v
+    // q,k: [B][H][T][64] split bf16 ; v transposed: [B][H][64][Tp] split bf16. Flat row m = b*T + t.
+    int qkv_mode;
+    int T, Tp, H, D;
+    float q_scale;
+    __nv_bfloat16 *q_hi, *q_lo, *k_hi, *k_lo, *vt_hi, *vt_lo;
+};
+
+// Launch on `stream`. Returns cudaGetLastError() of the launch.
+cudaError_t launch_gemm_bf16x3(const GemmParams& p, int sm_count, cudaStream_t stream);
+
+// Encode a 3-D bf16 tensor map with the 128B swizzle. strides in ELEMENTS for dims 1 and 2.
+// Returns 0 on success, else a CUresult / -1 (driver entry point missing).
+int encode_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
+                        uint64_t stride2, uint32_t box0, uint32_t box1);
+
+}  // namespace s3b

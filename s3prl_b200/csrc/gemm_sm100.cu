@@ -1,0 +1,350 @@
+// Persistent, warp-specialised tcgen05 GEMM with error-compensated bf16 operands (3 MMAs per product):
+//   D[m][n] = sum_k A[m][k] * W[n][k],  A = A_hi + A_lo, W = W_hi + W_lo (bf16),  fp32 accumulation in TMEM
+//   D += A_hi*W_hi + A_hi*W_lo + A_lo*W_hi
+//
+// Replaces the reference's fp32 torch ops (cited per call site in model.cu):
+//   nn.Conv1d(512,512,k,2) blocks      s3prl/upstream/wav2vec2/wav2vec2_model.py:2879,2927-2934
+//   post_extract_proj                  s3prl/upstream/hubert/hubert_model.py:489-490
+//   pos_conv (grouped Conv1d k=128)    s3prl/upstream/wav2vec2/wav2vec2_model.py:2937-2953,3064-3067
+//   q/k/v/out projections, fc1, fc2    s3prl/upstream/wav2vec2/wav2vec2_model.py:1146-1168,3260-3322
+//
+// Roles (256 threads, one CTA per SM, persistent over output tiles):
+//   warp 0 lane 0 : TMA producer  (A_hi, A_lo, W_hi, W_lo boxes -> 128B-swizzled smem ring)
+//   warp 1 lane 0 : MMA issuer    (tcgen05.mma kind::f16, M=128, N=umma_n, K=16 per instruction)
+//   warp 2        : TMEM allocator (512 columns = two 128 x 256 fp32 accumulator stages)
+//   warps 4..7    : epilogue      (tcgen05.ld -> bias / GELU / residual / mask -> fp32 and/or bf16 hi+lo stores)
+#include <stdio.h>
+
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace s3b {
+
+static constexpr int kBlockM = 128;
+static constexpr int kBlockK = 64;               // bf16 elements = one 128-byte swizzle row
+static constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
+static constexpr int kAccCols = 256;             // TMEM columns per accumulator stage
+static constexpr int kThreads = 256;
+
+template <int BLOCK_N>
+struct GemmCfg {
+    static constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
+    static constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;
+    static constexpr int kStages = (BLOCK_N >= 256) ? 2 : (BLOCK_N >= 128 ? 3 : 4);
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void store_f32x32(float* dst, const float (&x)[32]) {
+    float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d4[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+}
+
+template <int NC>
+__device__ __forceinline__ void store_split(__nv_bfloat16* dhi, __nv_bfloat16* dlo, const float (&x)[NC]) {
+    uint32_t h[NC / 2], l[NC / 2];
+#pragma unroll
+    for (int j = 0; j < NC / 2; ++j) split_pack2(x[2 * j], x[2 * j + 1], h[j], l[j]);
+    uint4* h4 = reinterpret_cast<uint4*>(dhi);
+    uint4* l4 = reinterpret_cast<uint4*>(dlo);
+#pragma unroll
+    for (int j = 0; j < NC / 8; ++j) {
+        h4[j] = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+        l4[j] = make_uint4(l[4 * j], l[4 * j + 1], l[4 * j + 2], l[4 * j + 3]);
+    }
+}
+
+// Epilogue for NC (16 or 32) consecutive accumulator columns of one output row.
+template <int NC>
+__device__ __forceinline__ void epilogue_cols(const GemmParams& p, const uint32_t (&v)[NC], bool row_ok, size_t m,
+                                              int col, bool masked) {
+    float x[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) x[j] = __uint_as_float(v[j]);
+    if (p.bias != nullptr) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+        for (int j = 0; j < NC / 4; ++j) {
+            const float4 b = __ldg(b4 + j);
+            x[4 * j] += b.x, x[4 * j + 1] += b.y, x[4 * j + 2] += b.z, x[4 * j + 3] += b.w;
+        }
+    }
+    if (p.gelu) {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) x[j] = gelu_erf(x[j]);
+    }
+    if (!row_ok) return;
+
+    if (p.qkv_mode) {
+        // m = b*T + t ; col = which*D + h*64 + d  (NC-aligned chunks never straddle a head)
+        const int b = (int)(m / (size_t)p.T);
+        const int t = (int)(m - (size_t)b * p.T);
+        const int which = col / p.D;
+        const int within = col - which * p.D;
+        const int h = within >> 6;
+        const int d = within & 63;
+        const size_t bh = (size_t)b * p.H + h;
+        if (which < 2) {
+            if (which == 0) {
+#pragma unroll
+                for (int j = 0; j < NC; ++j) x[j] *= p.q_scale;
+            }
+            __nv_bfloat16* dh = (which == 0 ? p.q_hi : p.k_hi) + (bh * p.T + t) * 64 + d;
+            __nv_bfloat16* dl = (which == 0 ? p.q_lo : p.k_lo) + (bh * p.T + t) * 64 + d;
+            store_split<NC>(dh, dl, x);
+        } else {
+            __nv_bfloat16* dh = p.vt_hi + (bh * 64 + d) * (size_t)p.Tp + t;
+            __nv_bfloat16* dl = p.vt_lo + (bh * 64 + d) * (size_t)p.Tp + t;
+#pragma unroll
+            for (int j = 0; j < NC; ++j) {
+                __nv_bfloat16 hi, lo;
+                split_bf16(x[j], hi, lo);
+                dh[(size_t)j * p.Tp] = hi;
+                dl[(size_t)j * p.Tp] = lo;
+            }
+        }
+        return;
+    }
+
+    const size_t off = m * (size_t)p.ldo + col;
+    if (p.residual != nullptr) {
+        const float4* r4 = reinterpret_cast<const float4*>(p.residual + off);
+#pragma unroll
+        for (int j = 0; j < NC / 4; ++j) {
+            const float4 r = r4[j];
+            x[4 * j] += r.x, x[4 * j + 1] += r.y, x[4 * j + 2] += r.z, x[4 * j + 3] += r.w;
+        }
+    }
+    if (masked) {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) x[j] = 0.0f;
+    }
+    if (p.out_f32 != nullptr) {
+        float4* d4 = reinterpret_cast<float4*>(p.out_f32 + off);
+#pragma unroll
+        for (int j = 0; j < NC / 4; ++j) d4[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+    }
+    if (p.out_hi != nullptr) store_split<NC>(p.out_hi + off, p.out_lo + off, x);
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1) gemm_bf16x3_kernel(const __grid_constant__ GemmParams p) {
+    using Cfg = GemmCfg<BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment is required by the 128B swizzle atoms (8 rows x 128 B)
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t* full_bar = bars;                       // [kStages]
+    uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
+    uint64_t* tmem_full = bars + 2 * Cfg::kStages;   // [2]
+    uint64_t* tmem_empty = tmem_full + 2;            // [2]
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.a_hi);
+        tma_prefetch_desc(&p.a_lo);
+        tma_prefetch_desc(&p.b_hi);
+        tma_prefetch_desc(&p.b_lo);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < Cfg::kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tmem_full[s], 1);
+            mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_base_slot, 2 * kAccCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    const int tiles_m = p.batches * p.tiles_m_per_batch;
+    const int num_tiles = tiles_m * p.n_tiles;
+    const uint32_t b_tile_bytes = (uint32_t)p.umma_n * kBlockK * 2;
+    const uint32_t stage_tx_bytes = 2u * kATileBytes + 2u * b_tile_bytes;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int n_tile = tile % p.n_tiles;
+                const int mt = tile / p.n_tiles;
+                const int batch = mt / p.tiles_m_per_batch;
+                const int row0 = (mt - batch * p.tiles_m_per_batch) * kBlockM;
+                const int a_k0 = p.a_k_per_ntile * n_tile;
+                const int b_n0 = p.b_n_tiled ? n_tile * p.umma_n : 0;
+                const int b_z0 = n_tile * p.b_z_per_ntile;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    const int kq = kb / p.kb_per_row;
+                    const int kr = kb - kq * p.kb_per_row;
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    uint8_t* st = smem + stage * Cfg::kStageBytes;
+                    mbar_arrive_expect_tx(&full_bar[stage], stage_tx_bytes);
+                    const int a_row = row0 + kq * p.a_row_step + p.a_row_off;
+                    tma_load_3d(st, &p.a_hi, &full_bar[stage], a_k0 + kr * kBlockK, a_row, batch);
+                    tma_load_3d(st + kATileBytes, &p.a_lo, &full_bar[stage], a_k0 + kr * kBlockK, a_row, batch);
+                    const int b_k = (p.b_k_linear ? kb : kr) * kBlockK;
+                    const int b_z = p.b_k_linear ? 0 : b_z0 + kq;
+                    tma_load_3d(st + 2 * kATileBytes, &p.b_hi, &full_bar[stage], b_k, b_n0, b_z);
+                    tma_load_3d(st + 2 * kATileBytes + Cfg::kBTileBytes, &p.b_lo, &full_bar[stage], b_k, b_n0, b_z);
+                    if (++stage == Cfg::kStages) stage = 0, phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(kBlockM, (uint32_t)p.umma_n);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccCols;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + stage * Cfg::kStageBytes);
+                    const uint64_t da_hi = make_smem_desc_sw128(st);
+                    const uint64_t da_lo = make_smem_desc_sw128(st + kATileBytes);
+                    const uint64_t db_hi = make_smem_desc_sw128(st + 2 * kATileBytes);
+                    const uint64_t db_lo = make_smem_desc_sw128(st + 2 * kATileBytes + Cfg::kBTileBytes);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        // advance 16 bf16 (= 32 bytes) along K inside the swizzle atom: +2 in (addr >> 4) units
+                        const uint64_t ko = (uint64_t)(k * 2);
+                        umma_bf16(d_tmem, da_lo + ko, db_hi + ko, idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_bf16(d_tmem, da_hi + ko, db_lo + ko, idesc, 1u);
+                        umma_bf16(d_tmem, da_hi + ko, db_hi + ko, idesc, 1u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+                    if (++stage == Cfg::kStages) stage = 0, phase ^= 1u;
+                }
+                umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+                if (++acc == 2) acc = 0, acc_phase ^= 1u;
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int ew = warp - 4;  // == warp % 4 : TMEM lane quadrant this warp may access
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int n_tile = tile % p.n_tiles;
+            const int mt = tile / p.n_tiles;
+            const int batch = mt / p.tiles_m_per_batch;
+            const int row0 = (mt - batch * p.tiles_m_per_batch) * kBlockM;
+            const int row = row0 + ew * 32 + lane;
+            const bool row_ok = row < p.rows_per_batch;
+            const size_t m = (size_t)batch * p.out_rows_per_batch + (row_ok ? row : 0);
+            const bool masked = (p.row_mask != nullptr) && row_ok && (p.row_mask[m] != 0);
+            const int col0 = n_tile * p.umma_n;
+
+            mbar_wait(&tmem_full[acc], acc_phase);
+            __syncwarp();
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * kAccCols;
+            int c = 0;
+            for (; c + 32 <= p.umma_n; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_row + (uint32_t)c, v);
+                tmem_ld_wait();
+                epilogue_cols<32>(p, v, row_ok, m, col0 + c, masked);
+            }
+            if (c < p.umma_n) {  // 16-column tail (umma_n % 32 == 16)
+                uint32_t v[16];
+                tmem_ld_32x16(t_row + (uint32_t)c, v);
+                tmem_ld_wait();
+                epilogue_cols<16>(p, v, row_ok, m, col0 + c, masked);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) acc = 0, acc_phase ^= 1u;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * kAccCols);
+    }
+}
+
+template <int BLOCK_N>
+static cudaError_t launch_impl(const GemmParams& p, int sm_count, cudaStream_t stream) {
+    using Cfg = GemmCfg<BLOCK_N>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16x3_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::kSmemBytes);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int num_tiles = p.batches * p.tiles_m_per_batch * p.n_tiles;
+    if (num_tiles <= 0) return cudaSuccess;
+    const int grid = num_tiles < sm_count ? num_tiles : sm_count;
+    gemm_bf16x3_kernel<BLOCK_N><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gemm_bf16x3(const GemmParams& p, int sm_count, cudaStream_t stream) {
+    if (p.umma_n % 16 != 0 || p.umma_n < 16 || p.umma_n > 256) return cudaErrorInvalidValue;
+    if (p.umma_n > 128) return launch_impl<256>(p, sm_count, stream);
+    if (p.umma_n > 64) return launch_impl<128>(p, sm_count, stream);
+    return launch_impl<64>(p, sm_count, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// tensor-map encoding through the driver entry point (no link-time libcuda dependency: the C-ABI
+// library must load on a GPU-less host for the symbol-export test)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+    }
+    return fn;
+}
+
+int encode_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
+                        uint64_t stride2, uint32_t box0, uint32_t box1) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (fn == nullptr) return -1;
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {stride1 * 2, stride2 * 2};  // bytes
+    cuuint32_t box[3] = {box0, box1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return (int)r;
+}
+
+}  // namespace s3b

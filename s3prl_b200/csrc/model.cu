@@ -1,0 +1,860 @@
+// Host-side orchestration of the upstream forward + the C ABI (include/s3prl_b200.h).
+//
+// Reference call stack being replaced:
+//   UpstreamExpert.forward                      s3prl/upstream/hubert/expert.py:56-72
+//   HubertModel.forward / extract_features      s3prl/upstream/hubert/hubert_model.py:466-513,566-582
+//   ConvFeatureExtractionModel.forward          s3prl/upstream/wav2vec2/wav2vec2_model.py:2927-2934
+//   TransformerEncoder.extract_features         s3prl/upstream/wav2vec2/wav2vec2_model.py:3054-3121
+//   TransformerSentenceEncoderLayer.forward     s3prl/upstream/wav2vec2/wav2vec2_model.py:3260-3322
+//   WavLM TransformerEncoder / layer            s3prl/upstream/wavlm/WavLM.py:599-645,709-774
+// Data layout in HBM: every activation is token-major / channels-last ([B][L][C]); GEMM operands are kept as
+// two bf16 planes (hi, lo); hidden states are written once, in fp32, straight into the caller's
+// [NL+1][B][T][D] buffer (the reference's forward hooks become plain views of that buffer).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/s3prl_b200.h"
+#include "gemm.cuh"
+#include "kernels.cuh"
+#include "wavlm.cuh"
+
+using namespace s3b;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return 1;
+}
+#define CUDA_OK(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                           __FILE__, __LINE__);                                    \
+    } while (0)
+#define S3B_OK(expr)            \
+    do {                        \
+        int _r = (expr);        \
+        if (_r != 0) return _r; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// containers
+// ------------------------------------------------------------------------------------------------
+struct HostTensor {
+    std::vector<int64_t> shape;
+    std::vector<float> data;
+    size_t numel() const { return data.size(); }
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t n) {
+        n += 1 << 16;  // slack: TMA boxes may over-read the last rows of a view (never consumed)
+        if (n <= bytes) return 0;
+        if (p) cudaFree(p);
+        p = nullptr, bytes = 0;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e != cudaSuccess) return fail("cudaMalloc(%zu) failed: %s", n, cudaGetErrorString(e));
+        // zero once so that never-written padding is finite (0 * garbage must not be NaN)
+        e = cudaMemset(p, 0, n);
+        if (e != cudaSuccess) return fail("cudaMemset failed: %s", cudaGetErrorString(e));
+        bytes = n;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr, bytes = 0;
+    }
+    template <class T>
+    T* as() const {
+        return reinterpret_cast<T*>(p);
+    }
+};
+
+struct SplitBuf {  // bf16 hi / lo planes
+    DevBuf hi, lo;
+    int ensure(size_t elems) {
+        S3B_OK(hi.ensure(elems * 2));
+        return lo.ensure(elems * 2);
+    }
+    __nv_bfloat16* h() const { return hi.as<__nv_bfloat16>(); }
+    __nv_bfloat16* l() const { return lo.as<__nv_bfloat16>(); }
+    void release() { hi.release(), lo.release(); }
+};
+
+static const int kNumConv = 7;
+static const int kConvK[kNumConv] = {10, 3, 3, 3, 3, 2, 2};
+static const int kConvS[kNumConv] = {5, 2, 2, 2, 2, 2, 2};
+static const int kConvDim = 512;
+
+struct LayerW {
+    SplitBuf qkv, out, fc1, fc2;
+    DevBuf qkv_b, out_b, fc1_b, fc2_b, ln1_g, ln1_b, ln2_g, ln2_b;
+    DevBuf grep_w, grep_b, grep_a;  // WavLM gate
+};
+
+struct s3b_model {
+    s3b_config cfg;
+    std::map<std::string, HostTensor> host;
+    bool finalized = false;
+    int sm_count = 148;
+
+    // weights
+    DevBuf conv0_w, conv0_b, norm0_g, norm0_b;           // conv 0 (+ GroupNorm or LN affine)
+    SplitBuf conv_w[kNumConv];                             // 1..6, [512][kw*512] (tap-major K)
+    DevBuf conv_b[kNumConv], conv_ln_g[kNumConv], conv_ln_b[kNumConv];
+    DevBuf ln512_g, ln512_b, proj_b, pos_b, enc_ln_g, enc_ln_b;
+    SplitBuf proj_w, pos_w;
+    DevBuf rel_table_src;  // WavLM relative_attention_bias.weight [num_buckets][H]
+    std::vector<LayerW> layers;
+
+    // workspace (grown on demand, reused across calls)
+    DevBuf wav_ptrs, lens_dev, kvlen_dev, rowmask_dev, wav_stats, wav_pad;
+    DevBuf c0_part, c0_ss, conv_f32, tmp_f32, x_f32, x1_f32, gate, rel_table;
+    SplitBuf act[kNumConv], ln512_s, x_s, xs_s, q_s, k_s, vt_s, ctx_s, x1_s, h_s;
+    DevBuf stage_wav, stage_out;  // s3b_forward_host staging
+    std::vector<long long> lens_host;
+    std::vector<int> kv_host;
+    std::vector<uint8_t> mask_host;
+    int rel_table_T = -1;
+};
+
+// ------------------------------------------------------------------------------------------------
+// host helpers
+// ------------------------------------------------------------------------------------------------
+static int upload_f32(DevBuf& dst, const float* src, size_t n) {
+    S3B_OK(dst.ensure(n * 4));
+    CUDA_OK(cudaMemcpy(dst.p, src, n * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+static int upload_split(SplitBuf& dst, const float* src, size_t n) {
+    DevBuf tmp;
+    S3B_OK(upload_f32(tmp, src, n));
+    S3B_OK(dst.ensure(n));
+    CUDA_OK(launch_split(tmp.as<float>(), dst.h(), dst.l(), n, 0));
+    CUDA_OK(cudaDeviceSynchronize());
+    tmp.release();
+    return 0;
+}
+static const HostTensor* find(const s3b_model* m, const std::string& k) {
+    auto it = m->host.find(k);
+    return it == m->host.end() ? nullptr : &it->second;
+}
+static int need(const s3b_model* m, const std::string& k, std::initializer_list<int64_t> shape, const HostTensor** out) {
+    const HostTensor* t = find(m, k);
+    if (!t) return fail("missing tensor '%s'", k.c_str());
+    std::vector<int64_t> want(shape);
+    if (t->shape != want) {
+        std::string got, exp;
+        for (auto d : t->shape) got += std::to_string(d) + ",";
+        for (auto d : want) exp += std::to_string(d) + ",";
+        return fail("tensor '%s' has shape [%s], expected [%s]", k.c_str(), got.c_str(), exp.c_str());
+    }
+    *out = t;
+    return 0;
+}
+static int upload_vec(s3b_model* m, const std::string& k, int64_t n, DevBuf& dst) {
+    const HostTensor* t;
+    S3B_OK(need(m, k, {n}, &t));
+    return upload_f32(dst, t->data.data(), (size_t)n);
+}
+
+static int64_t conv_out_len(int64_t L, int i) { return L < kConvK[i] ? 0 : (L - kConvK[i]) / kConvS[i] + 1; }
+
+static int64_t num_frames(int64_t L) {
+    for (int i = 0; i < kNumConv; ++i) L = conv_out_len(L, i);
+    return L;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: library
+// ------------------------------------------------------------------------------------------------
+extern "C" int s3b_version(void) { return 100; }
+extern "C" const char* s3b_last_error(void) { return g_last_error.c_str(); }
+extern "C" int s3b_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: model lifetime
+// ------------------------------------------------------------------------------------------------
+extern "C" int s3b_model_create(const s3b_config* cfg, s3b_model** out) {
+    if (!cfg || !out) return fail("null argument");
+    if (cfg->embed_dim % 128 != 0 || cfg->embed_dim > 1280) return fail("embed_dim must be a multiple of 128, <= 1280");
+    if (cfg->num_heads * 64 != cfg->embed_dim) return fail("head dim must be 64");
+    if (cfg->ffn_dim % 256 != 0) return fail("ffn_dim must be a multiple of 256");
+    if (cfg->embed_dim % cfg->pos_conv_groups != 0) return fail("embed_dim %% pos_conv_groups != 0");
+    const int cpg = cfg->embed_dim / cfg->pos_conv_groups;
+    if (cpg % 16 != 0 || cpg > 64) return fail("channels per pos_conv group must be a multiple of 16, <= 64");
+    if (cfg->pos_conv_kernel % 2 != 0) return fail("pos_conv_kernel must be even");
+    if (cfg->num_layers < 1 || cfg->num_layers > 63) return fail("num_layers out of range");
+    s3b_model* m = new s3b_model();
+    m->cfg = *cfg;
+    *out = m;
+    return 0;
+}
+
+extern "C" int s3b_model_set_tensor(s3b_model* m, const char* name, const float* data, const int64_t* shape,
+                                    int32_t ndim) {
+    if (!m || !name || !data || (!shape && ndim > 0)) return fail("null argument");
+    if (m->finalized) return fail("model already finalized");
+    HostTensor t;
+    size_t n = 1;
+    for (int i = 0; i < ndim; ++i) t.shape.push_back(shape[i]), n *= (size_t)shape[i];
+    t.data.assign(data, data + n);
+    m->host[name] = std::move(t);
+    return 0;
+}
+
+extern "C" void s3b_model_destroy(s3b_model* m) {
+    if (!m) return;
+    DevBuf* bufs[] = {&m->conv0_w, &m->conv0_b, &m->norm0_g, &m->norm0_b, &m->ln512_g, &m->ln512_b, &m->proj_b,
+                      &m->pos_b, &m->enc_ln_g, &m->enc_ln_b, &m->rel_table_src, &m->wav_ptrs, &m->lens_dev,
+                      &m->kvlen_dev, &m->rowmask_dev, &m->wav_stats, &m->wav_pad, &m->c0_part, &m->c0_ss,
+                      &m->conv_f32, &m->tmp_f32, &m->x_f32, &m->x1_f32, &m->gate, &m->rel_table, &m->stage_wav,
+                      &m->stage_out};
+    for (DevBuf* b : bufs) b->release();
+    for (int i = 0; i < kNumConv; ++i) {
+        m->conv_w[i].release(), m->conv_b[i].release(), m->conv_ln_g[i].release(), m->conv_ln_b[i].release();
+        m->act[i].release();
+    }
+    SplitBuf* sb[] = {&m->proj_w, &m->pos_w, &m->ln512_s, &m->x_s, &m->xs_s, &m->q_s, &m->k_s, &m->vt_s, &m->ctx_s,
+                      &m->x1_s, &m->h_s};
+    for (SplitBuf* b : sb) b->release();
+    for (LayerW& l : m->layers) {
+        l.qkv.release(), l.out.release(), l.fc1.release(), l.fc2.release();
+        DevBuf* lb[] = {&l.qkv_b, &l.out_b, &l.fc1_b, &l.fc2_b, &l.ln1_g, &l.ln1_b, &l.ln2_g, &l.ln2_b,
+                        &l.grep_w, &l.grep_b, &l.grep_a};
+        for (DevBuf* b : lb) b->release();
+    }
+    delete m;
+}
+
+extern "C" int s3b_model_finalize(s3b_model* m) {
+    if (!m) return fail("null model");
+    if (m->finalized) return 0;
+    if (s3b_device_count() == 0) return fail("no CUDA device: s3prl_b200 has no CPU fallback");
+    int dev = 0;
+    CUDA_OK(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) return fail("device is sm_%d%d; this library contains sm_100a code only", prop.major, prop.minor);
+    m->sm_count = prop.multiProcessorCount;
+
+    const s3b_config& c = m->cfg;
+    const int D = c.embed_dim, F = c.ffn_dim, C = kConvDim;
+    const HostTensor* t;
+    const std::string fe = "feature_extractor.conv_layers.";
+
+    // ---- conv 0 ------------------------------------------------------------------------------
+    S3B_OK(need(m, fe + "0.0.weight", {C, 1, kConvK[0]}, &t));
+    S3B_OK(upload_f32(m->conv0_w, t->data.data(), t->numel()));
+    if (c.conv_bias) S3B_OK(upload_vec(m, fe + "0.0.bias", C, m->conv0_b));
+    if (c.extractor_layer_norm) {
+        S3B_OK(upload_vec(m, fe + "0.2.1.weight", C, m->norm0_g));
+        S3B_OK(upload_vec(m, fe + "0.2.1.bias", C, m->norm0_b));
+    } else {
+        S3B_OK(upload_vec(m, fe + "0.2.weight", C, m->norm0_g));
+        S3B_OK(upload_vec(m, fe + "0.2.bias", C, m->norm0_b));
+    }
+    // ---- conv 1..6: [out][in][tap] -> [out][tap*512 + in] (K index of the channels-last im2col row) ----
+    for (int i = 1; i < kNumConv; ++i) {
+        const std::string p = fe + std::to_string(i);
+        const int kw = kConvK[i];
+        S3B_OK(need(m, p + ".0.weight", {C, C, kw}, &t));
+        std::vector<float> r((size_t)C * C * kw);
+        for (int o = 0; o < C; ++o)
+            for (int ci = 0; ci < C; ++ci)
+                for (int j = 0; j < kw; ++j) r[((size_t)o * kw + j) * C + ci] = t->data[((size_t)o * C + ci) * kw + j];
+        S3B_OK(upload_split(m->conv_w[i], r.data(), r.size()));
+        if (c.conv_bias) S3B_OK(upload_vec(m, p + ".0.bias", C, m->conv_b[i]));
+        if (c.extractor_layer_norm) {
+            S3B_OK(upload_vec(m, p + ".2.1.weight", C, m->conv_ln_g[i]));
+            S3B_OK(upload_vec(m, p + ".2.1.bias", C, m->conv_ln_b[i]));
+        }
+    }
+    // ---- LayerNorm(512) + post_extract_proj ----------------------------------------------------------
+    S3B_OK(upload_vec(m, "layer_norm.weight", C, m->ln512_g));
+    S3B_OK(upload_vec(m, "layer_norm.bias", C, m->ln512_b));
+    S3B_OK(need(m, "post_extract_proj.weight", {D, C}, &t));
+    S3B_OK(upload_split(m->proj_w, t->data.data(), t->numel()));
+    S3B_OK(upload_vec(m, "post_extract_proj.bias", D, m->proj_b));
+    // ---- pos_conv: fold weight_norm(dim=2): W[o][c][k] = g[k] * v[o][c][k] / ||v[:,:,k]||  ---------------
+    //      (make_conv_pos, wav2vec2_model.py:2937-2953). GEMM B operand: [group*Kp + tap][n = cpg][64 (zero padded)]
+    {
+        const int G = c.pos_conv_groups, cpg = D / G, Kp = c.pos_conv_kernel;
+        const HostTensor *tg, *tv;
+        S3B_OK(need(m, "encoder.pos_conv.0.weight_g", {1, 1, Kp}, &tg));
+        S3B_OK(need(m, "encoder.pos_conv.0.weight_v", {D, cpg, Kp}, &tv));
+        std::vector<double> nrm(Kp, 0.0);
+        for (size_t oc = 0; oc < (size_t)D * cpg; ++oc)
+            for (int k = 0; k < Kp; ++k) {
+                const double v = tv->data[oc * Kp + k];
+                nrm[k] += v * v;
+            }
+        std::vector<float> scale(Kp);
+        for (int k = 0; k < Kp; ++k) scale[k] = (float)((double)tg->data[k] / sqrt(nrm[k]));
+        std::vector<float> wb((size_t)G * Kp * cpg * 64, 0.0f);
+        for (int g = 0; g < G; ++g)
+            for (int k = 0; k < Kp; ++k)
+                for (int n = 0; n < cpg; ++n)
+                    for (int ci = 0; ci < cpg; ++ci) {
+                        const int o = g * cpg + n;
+                        // fp32 product like torch's _weight_norm (v * (g / norm))
+                        wb[(((size_t)g * Kp + k) * cpg + n) * 64 + ci] = tv->data[((size_t)o * cpg + ci) * Kp + k] * scale[k];
+                    }
+        S3B_OK(upload_split(m->pos_w, wb.data(), wb.size()));
+        S3B_OK(upload_vec(m, "encoder.pos_conv.0.bias", D, m->pos_b));
+    }
+    S3B_OK(upload_vec(m, "encoder.layer_norm.weight", D, m->enc_ln_g));
+    S3B_OK(upload_vec(m, "encoder.layer_norm.bias", D, m->enc_ln_b));
+    // ---- transformer layers ------------------------------------------------------------------------
+    m->layers.resize(c.num_layers);
+    for (int l = 0; l < c.num_layers; ++l) {
+        LayerW& L = m->layers[l];
+        const std::string p = "encoder.layers." + std::to_string(l) + ".";
+        const HostTensor *wq, *wk, *wv, *bq, *bk, *bv;
+        S3B_OK(need(m, p + "self_attn.q_proj.weight", {D, D}, &wq));
+        S3B_OK(need(m, p + "self_attn.k_proj.weight", {D, D}, &wk));
+        S3B_OK(need(m, p + "self_attn.v_proj.weight", {D, D}, &wv));
+        S3B_OK(need(m, p + "self_attn.q_proj.bias", {D}, &bq));
+        S3B_OK(need(m, p + "self_attn.k_proj.bias", {D}, &bk));
+        S3B_OK(need(m, p + "self_attn.v_proj.bias", {D}, &bv));
+        std::vector<float> w((size_t)3 * D * D), b((size_t)3 * D);
+        memcpy(w.data(), wq->data.data(), (size_t)D * D * 4);
+        memcpy(w.data() + (size_t)D * D, wk->data.data(), (size_t)D * D * 4);
+        memcpy(w.data() + (size_t)2 * D * D, wv->data.data(), (size_t)D * D * 4);
+        memcpy(b.data(), bq->data.data(), D * 4), memcpy(b.data() + D, bk->data.data(), D * 4);
+        memcpy(b.data() + 2 * D, bv->data.data(), D * 4);
+        S3B_OK(upload_split(L.qkv, w.data(), w.size()));
+        S3B_OK(upload_f32(L.qkv_b, b.data(), b.size()));
+        S3B_OK(need(m, p + "self_attn.out_proj.weight", {D, D}, &t));
+        S3B_OK(upload_split(L.out, t->data.data(), t->numel()));
+        S3B_OK(upload_vec(m, p + "self_attn.out_proj.bias", D, L.out_b));
+        S3B_OK(upload_vec(m, p + "self_attn_layer_norm.weight", D, L.ln1_g));
+        S3B_OK(upload_vec(m, p + "self_attn_layer_norm.bias", D, L.ln1_b));
+        S3B_OK(need(m, p + "fc1.weight", {F, D}, &t));
+        S3B_OK(upload_split(L.fc1, t->data.data(), t->numel()));
+        S3B_OK(upload_vec(m, p + "fc1.bias", F, L.fc1_b));
+        S3B_OK(need(m, p + "fc2.weight", {D, F}, &t));
+        S3B_OK(upload_split(L.fc2, t->data.data(), t->numel()));
+        S3B_OK(upload_vec(m, p + "fc2.bias", D, L.fc2_b));
+        S3B_OK(upload_vec(m, p + "final_layer_norm.weight", D, L.ln2_g));
+        S3B_OK(upload_vec(m, p + "final_layer_norm.bias", D, L.ln2_b));
+        if (c.relative_position && c.gru_rel_pos) {
+            S3B_OK(need(m, p + "self_attn.grep_linear.weight", {8, 64}, &t));
+            S3B_OK(upload_f32(L.grep_w, t->data.data(), t->numel()));
+            S3B_OK(upload_vec(m, p + "self_attn.grep_linear.bias", 8, L.grep_b));
+            S3B_OK(need(m, p + "self_attn.grep_a", {1, c.num_heads, 1, 1}, &t));
+            S3B_OK(upload_f32(L.grep_a, t->data.data(), t->numel()));
+        }
+    }
+    if (c.relative_position) {
+        S3B_OK(need(m, "encoder.layers.0.self_attn.relative_attention_bias.weight", {c.num_buckets, c.num_heads}, &t));
+        S3B_OK(upload_f32(m->rel_table_src, t->data.data(), t->numel()));
+    }
+    m->host.clear();
+    m->finalized = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// frame bookkeeping
+// ------------------------------------------------------------------------------------------------
+extern "C" int64_t s3b_num_frames(const s3b_model*, int64_t max_len) {
+    const int64_t T = num_frames(max_len);
+    return T > 0 ? T : -1;
+}
+
+extern "C" int s3b_valid_frames(const s3b_model* m, const int64_t* lens, int32_t batch, int64_t max_len,
+                                int32_t* valid) {
+    if (!m || !lens || !valid) return fail("null argument");
+    const int64_t T = num_frames(max_len);
+    if (T <= 0) return fail("max_len %lld too short for the conv stack", (long long)max_len);
+    bool any_pad = false;
+    for (int b = 0; b < batch; ++b) {
+        if (lens[b] < 1 || lens[b] > max_len) return fail("lens[%d]=%lld out of range", b, (long long)lens[b]);
+        any_pad |= lens[b] < max_len;
+    }
+    for (int b = 0; b < batch; ++b) {
+        int64_t v;
+        if (m->cfg.family == 1) {
+            // wav2vec2: conv-length rule, only when the batch has any padding (wav2vec2_model.py:2652-2671)
+            v = any_pad ? num_frames(lens[b]) : T;
+            if (v < 1) v = T;  // output_lengths - 1 == -1 indexes the last frame: every frame stays valid
+        } else {
+            // HuBERT / WavLM: frame t is padding iff all samples of chunk t are padding, chunk = Lmax // T
+            const int64_t chunk = max_len / T;
+            v = (lens[b] + chunk - 1) / chunk;
+        }
+        valid[b] = (int32_t)(v > T ? T : v);
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM descriptors
+// ------------------------------------------------------------------------------------------------
+struct Epi {
+    const float* bias = nullptr;
+    const float* residual = nullptr;
+    const uint8_t* row_mask = nullptr;
+    int gelu = 0;
+    float* out_f32 = nullptr;
+    __nv_bfloat16* out_hi = nullptr;
+    __nv_bfloat16* out_lo = nullptr;
+};
+
+static void set_epi(GemmParams& p, const Epi& e, int ldo) {
+    p.bias = e.bias, p.residual = e.residual, p.row_mask = e.row_mask, p.gelu = e.gelu;
+    p.out_f32 = e.out_f32, p.out_hi = e.out_hi, p.out_lo = e.out_lo, p.ldo = ldo;
+    p.qkv_mode = 0;
+}
+
+static int pick_umma_n(int N) {
+    if (N % 256 == 0) return 256;
+    if (N % 192 == 0) return 192;
+    if (N % 128 == 0) return 128;
+    if (N % 64 == 0) return 64;
+    if (N % 32 == 0) return 32;
+    return 16;
+}
+
+#define TMAP_OK(expr)                                                                     \
+    do {                                                                                  \
+        int _r = (expr);                                                                  \
+        if (_r != 0) return fail("cuTensorMapEncodeTiled failed (%d) at %s:%d", _r, __FILE__, __LINE__); \
+    } while (0)
+
+// out[M][N] = A[M][K] * W[N][K]^T, flat token-major A (hi/lo planes), K % 64 == 0
+static int linear_params(GemmParams& p, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo,
+                         const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int64_t M, int N, int K) {
+    memset(&p, 0, sizeof(p));
+    if (K % 64 != 0 || N % 16 != 0) return fail("linear: K %% 64 or N %% 16 violated (N=%d K=%d)", N, K);
+    const int un = pick_umma_n(N);
+    TMAP_OK(encode_tmap_bf16_3d(&p.a_hi, a_hi, K, M, 1, K, (uint64_t)M * K, 64, 128));
+    TMAP_OK(encode_tmap_bf16_3d(&p.a_lo, a_lo, K, M, 1, K, (uint64_t)M * K, 64, 128));
+    TMAP_OK(encode_tmap_bf16_3d(&p.b_hi, w_hi, K, N, 1, K, (uint64_t)N * K, 64, un));
+    TMAP_OK(encode_tmap_bf16_3d(&p.b_lo, w_lo, K, N, 1, K, (uint64_t)N * K, 64, un));
+    p.batches = 1, p.rows_per_batch = (int)M, p.tiles_m_per_batch = (int)((M + 127) / 128);
+    p.n_tiles = N / un, p.umma_n = un, p.num_k_blocks = K / 64, p.kb_per_row = K / 64;
+    p.a_row_step = 0, p.a_row_off = 0, p.a_k_per_ntile = 0, p.b_n_tiled = 1, p.b_z_per_ntile = 0;
+    p.out_rows_per_batch = (int)M;
+    return 0;
+}
+
+// conv i (k in {2,3}, stride 2) over channels-last [B][Lin][512]: row t of the [ceil(Lin/2)][1024] view holds
+// samples (2t, 2t+1); taps 0,1 come from view row t, tap 2 from the first half of view row t+1.
+static int conv_params(GemmParams& p, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const __nv_bfloat16* w_hi,
+                       const __nv_bfloat16* w_lo, int B, int64_t Lin, int64_t Lout, int kw) {
+    memset(&p, 0, sizeof(p));
+    const int C = kConvDim, K = kw * C;
+    const uint64_t rows = (uint64_t)((Lin + 1) / 2);
+    TMAP_OK(encode_tmap_bf16_3d(&p.a_hi, a_hi, 2 * C, rows, B, 2 * C, (uint64_t)Lin * C, 64, 128));
+    TMAP_OK(encode_tmap_bf16_3d(&p.a_lo, a_lo, 2 * C, rows, B, 2 * C, (uint64_t)Lin * C, 64, 128));
+    // weights [512][K], K index = tap*512 + channel, read linearly along K
+    TMAP_OK(encode_tmap_bf16_3d(&p.b_hi, w_hi, K, C, 1, K, (uint64_t)C * K, 64, 256));
+    TMAP_OK(encode_tmap_bf16_3d(&p.b_lo, w_lo, K, C, 1, K, (uint64_t)C * K, 64, 256));
+    p.batches = B, p.rows_per_batch = (int)Lout, p.tiles_m_per_batch = (int)((Lout + 127) / 128);
+    p.n_tiles = C / 256, p.umma_n = 256, p.num_k_blocks = K / 64, p.kb_per_row = (2 * C) / 64;
+    p.a_row_step = 1, p.a_row_off = 0, p.a_k_per_ntile = 0, p.b_n_tiled = 1, p.b_z_per_ntile = 0, p.b_k_linear = 1;
+    p.out_rows_per_batch = (int)Lout;
+    return 0;
+}
+
+// grouped positional conv: one k-block per tap; A row coordinate = t + tap - K/2 (TMA zero-fills t<0, t>=T)
+static int posconv_params(GemmParams& p, const s3b_config& c, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo,
+                          const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int B, int T) {
+    memset(&p, 0, sizeof(p));
+    const int D = c.embed_dim, G = c.pos_conv_groups, cpg = D / G, Kp = c.pos_conv_kernel;
+    TMAP_OK(encode_tmap_bf16_3d(&p.a_hi, x_hi, D, T, B, D, (uint64_t)T * D, 64, 128));
+    TMAP_OK(encode_tmap_bf16_3d(&p.a_lo, x_lo, D, T, B, D, (uint64_t)T * D, 64, 128));
+    TMAP_OK(encode_tmap_bf16_3d(&p.b_hi, w_hi, 64, cpg, (uint64_t)G * Kp, 64, (uint64_t)cpg * 64, 64, cpg));
+    TMAP_OK(encode_tmap_bf16_3d(&p.b_lo, w_lo, 64, cpg, (uint64_t)G * Kp, 64, (uint64_t)cpg * 64, 64, cpg));
+    p.batches = B, p.rows_per_batch = T, p.tiles_m_per_batch = (T + 127) / 128;
+    p.n_tiles = G, p.umma_n = cpg, p.num_k_blocks = Kp, p.kb_per_row = 1;
+    p.a_row_step = 1, p.a_row_off = -(Kp / 2), p.a_k_per_ntile = cpg, p.b_n_tiled = 0, p.b_z_per_ntile = Kp;
+    p.out_rows_per_batch = T;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+static int forward_impl(s3b_model* m, const float* const* wavs_dev, const int64_t* lens, int B, int64_t Lmax,
+                        float* hidden_out, cudaStream_t st) {
+    const s3b_config& c = m->cfg;
+    const int D = c.embed_dim, F = c.ffn_dim, H = c.num_heads, NL = c.num_layers, C = kConvDim;
+    if (B < 1) return fail("empty batch");
+    int64_t L[kNumConv];
+    {
+        int64_t cur = Lmax;
+        for (int i = 0; i < kNumConv; ++i) cur = L[i] = conv_out_len(cur, i);
+    }
+    const int64_t T64 = L[kNumConv - 1];
+    if (T64 < 1) return fail("max_len %lld too short: the conv stack yields no frame", (long long)Lmax);
+    if ((int64_t)B * L[0] > 2000000000LL) return fail("batch too large for 32-bit tile indexing");
+    const int T = (int)T64;
+    const int64_t M = (int64_t)B * T;
+    const int Tp = (T + 7) & ~7;
+
+    // ---- host-side integer bookkeeping -> device -------------------------------------------------------
+    m->kv_host.resize(B);
+    S3B_OK(s3b_valid_frames(m, lens, B, Lmax, m->kv_host.data()));
+    m->lens_host.assign(lens, lens + B);
+    m->mask_host.assign((size_t)M, 0);
+    for (int b = 0; b < B; ++b)
+        for (int t = m->kv_host[b]; t < T; ++t) m->mask_host[(size_t)b * T + t] = 1;
+    S3B_OK(m->wav_ptrs.ensure(B * sizeof(void*)));
+    S3B_OK(m->lens_dev.ensure(B * sizeof(long long)));
+    S3B_OK(m->kvlen_dev.ensure(B * sizeof(int)));
+    S3B_OK(m->rowmask_dev.ensure((size_t)M));
+    CUDA_OK(cudaMemcpyAsync(m->wav_ptrs.p, wavs_dev, B * sizeof(void*), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(m->lens_dev.p, m->lens_host.data(), B * sizeof(long long), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(m->kvlen_dev.p, m->kv_host.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(m->rowmask_dev.p, m->mask_host.data(), (size_t)M, cudaMemcpyHostToDevice, st));
+
+    // ---- workspace ----------------------------------------------------------------------------------
+    S3B_OK(m->wav_pad.ensure((size_t)B * Lmax * 4));
+    S3B_OK(m->wav_stats.ensure((size_t)B * 2 * 4));
+    S3B_OK(m->c0_part.ensure(conv0_ws_part_floats(B, (int)L[0]) * 4));
+    S3B_OK(m->c0_ss.ensure((size_t)2 * B * C * 4));
+    for (int i = 0; i < kNumConv - 1; ++i) S3B_OK(m->act[i].ensure((size_t)B * L[i] * C));
+    S3B_OK(m->conv_f32.ensure((size_t)B * (c.extractor_layer_norm ? L[1] : L[6]) * C * 4));
+    S3B_OK(m->ln512_s.ensure((size_t)M * C));
+    S3B_OK(m->tmp_f32.ensure((size_t)M * D * 4));
+    S3B_OK(m->x_f32.ensure((size_t)M * D * 4));
+    S3B_OK(m->x1_f32.ensure((size_t)M * D * 4));
+    S3B_OK(m->x_s.ensure((size_t)M * D));
+    S3B_OK(m->xs_s.ensure((size_t)M * D));
+    S3B_OK(m->x1_s.ensure((size_t)M * D));
+    S3B_OK(m->ctx_s.ensure((size_t)M * D));
+    S3B_OK(m->q_s.ensure((size_t)M * D));
+    S3B_OK(m->k_s.ensure((size_t)M * D));
+    S3B_OK(m->vt_s.ensure((size_t)B * H * 64 * Tp));
+    S3B_OK(m->h_s.ensure((size_t)M * F));
+
+    // ---- waveform packing (+ normalisation) ------------------------------------------------------------
+    CUDA_OK(launch_wav_pack(m->wav_ptrs.as<const float*>(), m->lens_dev.as<long long>(), B, Lmax, c.normalize_wav,
+                            m->wav_stats.as<float>(), m->wav_pad.as<float>(), st));
+
+    // ---- conv 0 + norm + GELU -> act[0] (bf16 hi/lo, channels-last) -----------------------------------------
+    if (c.extractor_layer_norm) {
+        CUDA_OK(launch_conv0_layernorm(m->wav_pad.as<float>(), B, Lmax, (int)L[0], m->conv0_w.as<float>(),
+                                       c.conv_bias ? m->conv0_b.as<float>() : nullptr, m->norm0_g.as<float>(),
+                                       m->norm0_b.as<float>(), m->act[0].h(), m->act[0].l(), st));
+    } else {
+        if (c.conv_bias) return fail("conv_bias with extractor_mode=default is not supported");
+        CUDA_OK(launch_conv0_groupnorm(m->wav_pad.as<float>(), B, Lmax, (int)L[0], m->conv0_w.as<float>(),
+                                       m->norm0_g.as<float>(), m->norm0_b.as<float>(), m->c0_part.as<float>(),
+                                       m->c0_ss.as<float>(), m->act[0].h(), m->act[0].l(), st));
+    }
+
+    // ---- conv 1..6 as implicit GEMM -------------------------------------------------------------------
+    GemmParams p;
+    for (int i = 1; i < kNumConv; ++i) {
+        S3B_OK(conv_params(p, m->act[i - 1].h(), m->act[i - 1].l(), m->conv_w[i].h(), m->conv_w[i].l(), B, L[i - 1],
+                           L[i], kConvK[i]));
+        Epi e;
+        e.bias = c.conv_bias ? m->conv_b[i].as<float>() : nullptr;
+        const bool last = (i == kNumConv - 1);
+        if (c.extractor_layer_norm) {
+            e.out_f32 = m->conv_f32.as<float>();
+        } else {
+            e.gelu = 1;
+            if (last) e.out_f32 = m->conv_f32.as<float>();
+            else e.out_hi = m->act[i].h(), e.out_lo = m->act[i].l();
+        }
+        set_epi(p, e, C);
+        CUDA_OK(launch_gemm_bf16x3(p, m->sm_count, st));
+        if (c.extractor_layer_norm) {
+            // per-frame LayerNorm(512) + GELU (wav2vec2_model.py:2887-2897)
+            CUDA_OK(launch_layernorm(m->conv_f32.as<float>(), (size_t)B * L[i], C, m->conv_ln_g[i].as<float>(),
+                                     m->conv_ln_b[i].as<float>(), 1, last ? m->conv_f32.as<float>() : nullptr,
+                                     last ? nullptr : m->act[i].h(), last ? nullptr : m->act[i].l(), st));
+        }
+    }
+
+    // ---- LayerNorm(512) -> post_extract_proj (+ zero padded frames) ------------------------------------------
+    CUDA_OK(launch_layernorm(m->conv_f32.as<float>(), (size_t)M, C, m->ln512_g.as<float>(), m->ln512_b.as<float>(), 0,
+                             nullptr, m->ln512_s.h(), m->ln512_s.l(), st));
+    {
+        S3B_OK(linear_params(p, m->ln512_s.h(), m->ln512_s.l(), m->proj_w.h(), m->proj_w.l(), M, D, C));
+        Epi e;
+        e.bias = m->proj_b.as<float>();
+        e.row_mask = m->rowmask_dev.as<uint8_t>();  // x[padding_mask] = 0 (wav2vec2_model.py:3061-3062)
+        e.out_f32 = m->x_f32.as<float>();
+        e.out_hi = m->x_s.h(), e.out_lo = m->x_s.l();
+        set_epi(p, e, D);
+        CUDA_OK(launch_gemm_bf16x3(p, m->sm_count, st));
+    }
+
+    // ---- x = x + GELU(pos_conv(x)) ; post-LN models: LayerNorm -> hidden state 0 ------------------------------
+    float* hs0 = hidden_out;
+    const size_t hs_stride = (size_t)M * D;
+    {
+        S3B_OK(posconv_params(p, c, m->x_s.h(), m->x_s.l(), m->pos_w.h(), m->pos_w.l(), B, T));
+        Epi e;
+        e.bias = m->pos_b.as<float>();
+        e.gelu = 1;
+        e.residual = m->x_f32.as<float>();
+        e.out_f32 = c.layer_norm_first ? hs0 : m->tmp_f32.as<float>();
+        set_epi(p, e, D);
+        CUDA_OK(launch_gemm_bf16x3(p, m->sm_count, st));
+        if (!c.layer_norm_first)
+            CUDA_OK(launch_layernorm(m->tmp_f32.as<float>(), (size_t)M, D, m->enc_ln_g.as<float>(),
+                                     m->enc_ln_b.as<float>(), 0, hs0, m->xs_s.h(), m->xs_s.l(), st));
+    }
+
+    // ---- WavLM relative position table (ungated, shared by all layers; WavLM.py:622-632) -----------------------
+    const bool rel = c.relative_position != 0;
+    if (rel) {
+        S3B_OK(m->rel_table.ensure((size_t)H * (2 * T - 1) * 4));
+        S3B_OK(m->gate.ensure((size_t)B * H * T * 4));
+        if (m->rel_table_T != T) {
+            CUDA_OK(launch_wavlm_rel_table(m->rel_table_src.as<float>(), c.num_buckets, c.max_distance, H, T,
+                                           m->rel_table.as<float>(), st));
+            m->rel_table_T = T;
+        }
+    }
+
+    // ---- transformer layers -------------------------------------------------------------------------
+    for (int l = 0; l < NL; ++l) {
+        LayerW& W = m->layers[l];
+        float* hs_in = hidden_out + (size_t)l * hs_stride;        // layer input = hidden state l
+        float* hs_out = hidden_out + (size_t)(l + 1) * hs_stride;  // hidden state l+1
+        const bool last = (l == NL - 1);
+
+        if (c.layer_norm_first)  // xs = LN1(residual stream)
+            CUDA_OK(launch_layernorm(hs_in, (size_t)M, D, W.ln1_g.as<float>(), W.ln1_b.as<float>(), 0, nullptr,
+                                     m->xs_s.h(), m->xs_s.l(), st));
+        // QKV projection, scattered per head; q pre-scaled by head_dim^-0.5 (exact power of two)
+        S3B_OK(linear_params(p, m->xs_s.h(), m->xs_s.l(), W.qkv.h(), W.qkv.l(), M, 3 * D, D));
+        {
+            Epi e;
+            e.bias = W.qkv_b.as<float>();
+            set_epi(p, e, 3 * D);
+            p.qkv_mode = 1, p.T = T, p.Tp = Tp, p.H = H, p.D = D, p.q_scale = 0.125f;
+            p.q_hi = m->q_s.h(), p.q_lo = m->q_s.l(), p.k_hi = m->k_s.h(), p.k_lo = m->k_s.l();
+            p.vt_hi = m->vt_s.h(), p.vt_lo = m->vt_s.l();
+        }
+        CUDA_OK(launch_gemm_bf16x3(p, m->sm_count, st));
+
+        AttnParams ap;
+        memset(&ap, 0, sizeof(ap));
+        const uint64_t BH = (uint64_t)B * H;
+        TMAP_OK(encode_tmap_bf16_3d(&ap.q_hi, m->q_s.h(), 64, T, BH, 64, (uint64_t)T * 64, 64, 128));
+        TMAP_OK(encode_tmap_bf16_3d(&ap.q_lo, m->q_s.l(), 64, T, BH, 64, (uint64_t)T * 64, 64, 128));
+        TMAP_OK(encode_tmap_bf16_3d(&ap.k_hi, m->k_s.h(), 64, T, BH, 64, (uint64_t)T * 64, 64, 64));
+        TMAP_OK(encode_tmap_bf16_3d(&ap.k_lo, m->k_s.l(), 64, T, BH, 64, (uint64_t)T * 64, 64, 64));
+        TMAP_OK(encode_tmap_bf16_3d(&ap.vt_hi, m->vt_s.h(), T, 64, BH, Tp, (uint64_t)64 * Tp, 64, 64));
+        TMAP_OK(encode_tmap_bf16_3d(&ap.vt_lo, m->vt_s.l(), T, 64, BH, Tp, (uint64_t)64 * Tp, 64, 64));
+        ap.B = B, ap.H = H, ap.T = T, ap.D = D;
+        ap.kv_len = m->kvlen_dev.as<int>();
+        if (rel) {
+            ap.bias_table = m->rel_table.as<float>();
+            // gate from the layer's attention input (post-LN: hs_in; pre-LN: LN1 output) wavlm/modules.py:534-551
+            CUDA_OK(launch_wavlm_gate(m->xs_s.h(), m->xs_s.l(), (size_t)M, B, T, H, D,
+                                      c.gru_rel_pos ? W.grep_w.as<float>() : nullptr, W.grep_b.as<float>(),
+                                      W.grep_a.as<float>(), m->gate.as<float>(), st));
+            ap.gate = m->gate.as<float>();
+        }
+        ap.ctx_hi = m->ctx_s.h(), ap.ctx_lo = m->ctx_s.l();
+        CUDA_OK(launch_attention(ap, st));
+
+        // out_proj + residual
+        S3B_OK(linear_params(p, m->ctx_s.h(), m->ctx_s.l(), W.out.h(), W.out.l(), M, D, D));
+        {
+            Epi e;
+            e.bias = W.out_b.as<float>();
+            e.residual = hs_in;
+            e.out_f32 = c.layer_norm_first ? m->x1_f32.as<float>() : m->tmp_f32.as<float>();
+            set_epi(p, e, D);
+        }
+        CUDA_OK(launch_gemm_bf16x3(p, m->sm_count, st));
+        if (c.layer_norm_first)  // x1_s = LN2(r1), r1 = x1_f32
+            CUDA_OK(launch_layernorm(m->x1_f32.as<float>(), (size_t)M, D, W.ln2_g.as<float>(), W.ln2_b.as<float>(), 0,
+                                     nullptr, m->x1_s.h(), m->x1_s.l(), st));
+        else  // x1 = LN1(x + attn)
+            CUDA_OK(launch_layernorm(m->tmp_f32.as<float>(), (size_t)M, D, W.ln1_g.as<float>(), W.ln1_b.as<float>(), 0,
+                                     m->x1_f32.as<float>(), m->x1_s.h(), m->x1_s.l(), st));
+        // fc1 + GELU
+        S3B_OK(linear_params(p, m->x1_s.h(), m->x1_s.l(), W.fc1.h(), W.fc1.l(), M, F, D));
+        {
+            Epi e;
+            e.bias = W.fc1_b.as<float>();
+            e.gelu = 1;
+            e.out_hi = m->h_s.h(), e.out_lo = m->h_s.l();
+            set_epi(p, e, F);
+        }
+        CUDA_OK(launch_gemm_bf16x3(p, m->sm_count, st));
+        // fc2 + residual
+        S3B_OK(linear_params(p, m->h_s.h(), m->h_s.l(), W.fc2.h(), W.fc2.l(), M, D, F));
+        {
+            Epi e;
+            e.bias = W.fc2_b.as<float>();
+            e.residual = m->x1_f32.as<float>();
+            // pre-LN: the sum IS hidden state l+1 (un-normalised residual stream), except after the last layer
+            e.out_f32 = (c.layer_norm_first && !last) ? hs_out : m->tmp_f32.as<float>();
+            set_epi(p, e, D);
+        }
+        CUDA_OK(launch_gemm_bf16x3(p, m->sm_count, st));
+        if (c.layer_norm_first) {
+            if (last)  // encoder.layer_norm on the final output (wav2vec2_model.py:3049-3050)
+                CUDA_OK(launch_layernorm(m->tmp_f32.as<float>(), (size_t)M, D, m->enc_ln_g.as<float>(),
+                                         m->enc_ln_b.as<float>(), 0, hs_out, nullptr, nullptr, st));
+        } else {
+            CUDA_OK(launch_layernorm(m->tmp_f32.as<float>(), (size_t)M, D, W.ln2_g.as<float>(), W.ln2_b.as<float>(), 0,
+                                     hs_out, last ? nullptr : m->xs_s.h(), last ? nullptr : m->xs_s.l(), st));
+        }
+    }
+    return 0;
+}
+
+extern "C" int s3b_forward(s3b_model* m, const float* const* wavs, const int64_t* lens, int32_t batch,
+                           int64_t max_len, float* hidden_out, void* stream) {
+    if (!m || !wavs || !lens || !hidden_out) return fail("null argument");
+    if (!m->finalized) return fail("model not finalized");
+    return forward_impl(m, wavs, lens, batch, max_len, hidden_out, (cudaStream_t)stream);
+}
+
+extern "C" int s3b_forward_host(s3b_model* m, const float* const* wavs, const int64_t* lens, int32_t batch,
+                                int64_t max_len, float* hidden_out) {
+    if (!m || !wavs || !lens || !hidden_out) return fail("null argument");
+    if (!m->finalized) return fail("model not finalized");
+    const int64_t T = num_frames(max_len);
+    if (T < 1) return fail("max_len too short");
+    size_t total = 0;
+    for (int b = 0; b < batch; ++b) total += (size_t)lens[b];
+    S3B_OK(m->stage_wav.ensure(total * 4));
+    const size_t out_elems = (size_t)(m->cfg.num_layers + 1) * batch * T * m->cfg.embed_dim;
+    S3B_OK(m->stage_out.ensure(out_elems * 4));
+    std::vector<const float*> ptrs(batch);
+    size_t off = 0;
+    for (int b = 0; b < batch; ++b) {
+        float* d = m->stage_wav.as<float>() + off;
+        CUDA_OK(cudaMemcpyAsync(d, wavs[b], (size_t)lens[b] * 4, cudaMemcpyHostToDevice, 0));
+        ptrs[b] = d;
+        off += (size_t)lens[b];
+    }
+    S3B_OK(forward_impl(m, ptrs.data(), lens, batch, max_len, m->stage_out.as<float>(), 0));
+    CUDA_OK(cudaMemcpyAsync(hidden_out, m->stage_out.p, out_elems * 4, cudaMemcpyDeviceToHost, 0));
+    CUDA_OK(cudaStreamSynchronize(0));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Featurizer
+// ------------------------------------------------------------------------------------------------
+extern "C" int s3b_weighted_sum(const float* hs, int32_t num, int64_t n_per_layer, const float* w, float* out,
+                                void* stream) {
+    if (!hs || !w || !out) return fail("null argument");
+    CUDA_OK(launch_weighted_sum(hs, num, (size_t)n_per_layer, w, out, (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int s3b_weighted_sum_backward(const float* hs, int32_t num, int64_t n_per_layer, const float* grad_out,
+                                         float* grad_w, void* stream) {
+    if (!hs || !grad_out || !grad_w) return fail("null argument");
+    CUDA_OK(launch_weighted_sum_bwd(hs, num, (size_t)n_per_layer, grad_out, grad_w, (cudaStream_t)stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// building blocks for parity tests
+// ------------------------------------------------------------------------------------------------
+static int device_sm_count(int* out) {
+    int dev = 0;
+    CUDA_OK(cudaGetDevice(&dev));
+    CUDA_OK(cudaDeviceGetAttribute(out, cudaDevAttrMultiProcessorCount, dev));
+    return 0;
+}
+
+extern "C" int s3b_linear_f32(const float* a, const float* w, const float* bias, const float* residual, int64_t M,
+                              int32_t N, int32_t K, int32_t gelu, float* out, void* stream) {
+    if (!a || !w || !out) return fail("null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    int sms = 0;
+    S3B_OK(device_sm_count(&sms));
+    SplitBuf as, ws;
+    S3B_OK(as.ensure((size_t)M * K));
+    S3B_OK(ws.ensure((size_t)N * K));
+    CUDA_OK(launch_split(a, as.h(), as.l(), (size_t)M * K, st));
+    CUDA_OK(launch_split(w, ws.h(), ws.l(), (size_t)N * K, st));
+    GemmParams p;
+    int r = linear_params(p, as.h(), as.l(), ws.h(), ws.l(), M, N, K);
+    if (r == 0) {
+        Epi e;
+        e.bias = bias, e.residual = residual, e.gelu = gelu, e.out_f32 = out;
+        set_epi(p, e, N);
+        cudaError_t ce = launch_gemm_bf16x3(p, sms, st);
+        if (ce != cudaSuccess) r = fail("gemm launch failed: %s", cudaGetErrorString(ce));
+    }
+    cudaError_t se = cudaStreamSynchronize(st);
+    as.release(), ws.release();
+    if (r == 0 && se != cudaSuccess) return fail("gemm execution failed: %s", cudaGetErrorString(se));
+    return r;
+}
+
+extern "C" int s3b_layernorm_f32(const float* x, int64_t M, int32_t D, const float* gamma, const float* beta,
+                                 int32_t gelu, float* out, void* stream) {
+    if (!x || !gamma || !beta || !out) return fail("null argument");
+    CUDA_OK(launch_layernorm(x, (size_t)M, D, gamma, beta, gelu, out, nullptr, nullptr, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int s3b_attention_f32(const float* q, const float* k, const float* v, const int32_t* valid_frames,
+                                 int32_t B, int32_t T, int32_t H, float* out, void* stream) {
+    // Runs the production path: identity "QKV GEMM" is replaced by a scatter of the given q/k/v, then the
+    // tcgen05 attention kernel, then ctx hi+lo is recombined to fp32.
+    if (!q || !k || !v || !valid_frames || !out) return fail("null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = H * 64, Tp = (T + 7) & ~7;
+    const size_t M = (size_t)B * T;
+    SplitBuf qs, ks, vts, ctx;
+    DevBuf kv;
+    S3B_OK(qs.ensure(M * D));
+    S3B_OK(ks.ensure(M * D));
+    S3B_OK(vts.ensure((size_t)B * H * 64 * Tp));
+    S3B_OK(ctx.ensure(M * D));
+    S3B_OK(kv.ensure(B * sizeof(int)));
+    CUDA_OK(cudaMemcpyAsync(kv.p, valid_frames, B * sizeof(int), cudaMemcpyHostToDevice, st));
+    CUDA_OK(launch_qkv_scatter(q, k, v, B, T, Tp, H, 0.125f, qs.h(), qs.l(), ks.h(), ks.l(), vts.h(), vts.l(), st));
+    AttnParams ap;
+    memset(&ap, 0, sizeof(ap));
+    const uint64_t BH = (uint64_t)B * H;
+    TMAP_OK(encode_tmap_bf16_3d(&ap.q_hi, qs.h(), 64, T, BH, 64, (uint64_t)T * 64, 64, 128));
+    TMAP_OK(encode_tmap_bf16_3d(&ap.q_lo, qs.l(), 64, T, BH, 64, (uint64_t)T * 64, 64, 128));
+    TMAP_OK(encode_tmap_bf16_3d(&ap.k_hi, ks.h(), 64, T, BH, 64, (uint64_t)T * 64, 64, 64));
+    TMAP_OK(encode_tmap_bf16_3d(&ap.k_lo, ks.l(), 64, T, BH, 64, (uint64_t)T * 64, 64, 64));
+    TMAP_OK(encode_tmap_bf16_3d(&ap.vt_hi, vts.h(), T, 64, BH, Tp, (uint64_t)64 * Tp, 64, 64));
+    TMAP_OK(encode_tmap_bf16_3d(&ap.vt_lo, vts.l(), T, 64, BH, Tp, (uint64_t)64 * Tp, 64, 64));
+    ap.B = B, ap.H = H, ap.T = T, ap.D = D, ap.kv_len = kv.as<int>();
+    ap.ctx_hi = ctx.h(), ap.ctx_lo = ctx.l();
+    CUDA_OK(launch_attention(ap, st));
+    CUDA_OK(launch_unsplit(ctx.h(), ctx.l(), M * D, out, st));
+    cudaError_t se = cudaStreamSynchronize(st);
+    qs.release(), ks.release(), vts.release(), ctx.release(), kv.release();
+    if (se != cudaSuccess) return fail("attention execution failed: %s", cudaGetErrorString(se));
+    return 0;
+}

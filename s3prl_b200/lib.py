@@ -1,0 +1,119 @@
+"""ctypes binding of the C ABI declared in include/s3prl_b200.h.
+
+PyTorch is used only as the owner of device memory and streams: every call below passes raw
+``data_ptr()`` addresses and the current ``cudaStream_t`` to the shared library. There is no CPU
+fallback: on a host without a CUDA device, anything that computes raises ``S3BError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+from typing import Optional
+
+_LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libs3prl_b200.so"
+
+EXPORTED_SYMBOLS = [
+    "s3b_version",
+    "s3b_last_error",
+    "s3b_device_count",
+    "s3b_model_create",
+    "s3b_model_set_tensor",
+    "s3b_model_finalize",
+    "s3b_model_destroy",
+    "s3b_num_frames",
+    "s3b_valid_frames",
+    "s3b_forward",
+    "s3b_forward_host",
+    "s3b_weighted_sum",
+    "s3b_weighted_sum_backward",
+    "s3b_linear_f32",
+    "s3b_layernorm_f32",
+    "s3b_attention_f32",
+]
+
+
+class S3BError(RuntimeError):
+    pass
+
+
+class S3BConfig(C.Structure):
+    """Mirror of ``struct s3b_config``."""
+
+    _fields_ = [
+        ("family", C.c_int32),
+        ("extractor_layer_norm", C.c_int32),
+        ("conv_bias", C.c_int32),
+        ("layer_norm_first", C.c_int32),
+        ("normalize_wav", C.c_int32),
+        ("num_layers", C.c_int32),
+        ("embed_dim", C.c_int32),
+        ("ffn_dim", C.c_int32),
+        ("num_heads", C.c_int32),
+        ("pos_conv_kernel", C.c_int32),
+        ("pos_conv_groups", C.c_int32),
+        ("relative_position", C.c_int32),
+        ("num_buckets", C.c_int32),
+        ("max_distance", C.c_int32),
+        ("gru_rel_pos", C.c_int32),
+        ("reserved", C.c_int32 * 8),
+    ]
+
+
+FAMILY_HUBERT, FAMILY_WAV2VEC2, FAMILY_WAVLM = 0, 1, 2
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load the shared library (building is `__graft_entry__.build()` / `python -m s3prl_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise S3BError(
+            f"{_LIB_PATH} is missing: build it with `python s3prl_b200/build.py` (needs nvcc). "
+            "s3prl_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(str(_LIB_PATH))
+    vp, i32, i64, f32p = C.c_void_p, C.c_int32, C.c_int64, C.c_void_p
+    lib.s3b_version.restype = C.c_int
+    lib.s3b_last_error.restype = C.c_char_p
+    lib.s3b_device_count.restype = C.c_int
+    lib.s3b_model_create.argtypes = [C.POINTER(S3BConfig), C.POINTER(vp)]
+    lib.s3b_model_set_tensor.argtypes = [vp, C.c_char_p, vp, C.POINTER(i64), i32]
+    lib.s3b_model_finalize.argtypes = [vp]
+    lib.s3b_model_destroy.argtypes = [vp]
+    lib.s3b_model_destroy.restype = None
+    lib.s3b_num_frames.argtypes = [vp, i64]
+    lib.s3b_num_frames.restype = i64
+    lib.s3b_valid_frames.argtypes = [vp, C.POINTER(i64), i32, i64, C.POINTER(i32)]
+    lib.s3b_forward.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i32, i64, f32p, vp]
+    lib.s3b_forward_host.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i32, i64, f32p]
+    lib.s3b_weighted_sum.argtypes = [f32p, i32, i64, f32p, f32p, vp]
+    lib.s3b_weighted_sum_backward.argtypes = [f32p, i32, i64, f32p, f32p, vp]
+    lib.s3b_linear_f32.argtypes = [f32p, f32p, f32p, f32p, i64, i32, i32, i32, f32p, vp]
+    lib.s3b_layernorm_f32.argtypes = [f32p, i64, i32, f32p, f32p, i32, f32p, vp]
+    lib.s3b_attention_f32.argtypes = [f32p, f32p, f32p, C.POINTER(i32), i32, i32, i32, f32p, vp]
+    _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        msg = load().s3b_last_error()
+        raise S3BError(msg.decode() if msg else f"s3prl_b200 call failed with status {status}")
+
+
+def require_gpu() -> None:
+    if load().s3b_device_count() < 1:
+        raise S3BError("no CUDA device visible: s3prl_b200 has no CPU fallback")
+
+
+def current_stream_ptr() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream
