@@ -1,0 +1,214 @@
+"""TEST INFRASTRUCTURE — generates tests/golden/*.pt by EXECUTING THE REFERENCE (s3prl @ /root/reference).
+
+Run in the build container only (the reference does not travel to the GPU box):
+
+    PYTHONPATH=/root/reference python oracle/make_golden.py [--only hubert_base]
+
+For every architecture it
+  1. fabricates the deterministic checkpoint (s3prl_b200.upstream.weights.fabricate_state_dict, seed 0),
+  2. writes it in the reference's converted-checkpoint format and loads it with the reference's own
+     ``UpstreamExpert`` (s3prl/upstream/{hubert,wav2vec2,wavlm}/expert.py) — reference constructors, reference
+     ``load_state_dict``, reference forward and hooks,
+  3. runs ``expert(wavs)`` on seeded waveforms (equal-length and ragged batches, incl. a 0.05 s utterance),
+  4. stores a strided sub-sample of every hidden state plus per-layer norms (fixtures stay < ~1 MB each).
+Integer rules (frame masks, WavLM buckets, Featurizer lengths) are recorded exhaustively.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import tempfile
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+GOLDEN = ROOT / "tests" / "golden"
+
+from s3prl_b200.upstream.configs import ARCHS, CONV_LAYERS  # noqa: E402
+from s3prl_b200.upstream.weights import fabricate_state_dict  # noqa: E402
+
+# (architecture, list of waveform lengths per case, channel stride of the stored sub-sample)
+CASES = {
+    "hubert_base": ([[16000, 12345, 800], [8000, 8000]], 7),
+    "wav2vec2_base_960": ([[16000, 12345, 800], [8000, 8000]], 7),
+    "wavlm_base_plus": ([[16000, 12345, 800], [8000, 8000]], 7),
+    "wav2vec2_large_ll60k": ([[12000, 7001]], 13),
+    "wav2vec2_large_960": ([[12000, 7001]], 13),
+    "wavlm_large": ([[12000, 7001]], 13),
+    "hubert_large_ll60k": ([[12000, 7001]], 13),
+}
+
+
+def seeded_wavs(lens, seed):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randn(n, generator=g) for n in lens]
+
+
+def reference_expert(name: str, sd):
+    """Instantiate the reference's UpstreamExpert on a fabricated checkpoint."""
+    cfg = ARCHS[name]
+    model_cfg = dict(
+        extractor_mode=cfg.extractor_mode,
+        conv_bias=cfg.conv_bias,
+        layer_norm_first=cfg.layer_norm_first,
+        encoder_layers=cfg.encoder_layers,
+        encoder_embed_dim=cfg.encoder_embed_dim,
+        encoder_ffn_embed_dim=cfg.encoder_ffn_embed_dim,
+        encoder_attention_heads=cfg.encoder_attention_heads,
+        conv_feature_layers=str(CONV_LAYERS),
+        conv_pos=cfg.conv_pos,
+        conv_pos_groups=cfg.conv_pos_groups,
+        activation_fn="gelu",
+        dropout=0.1,
+        attention_dropout=0.1,
+        encoder_layerdrop=0.05,
+    )
+    tmp = tempfile.NamedTemporaryFile(suffix=".pt", delete=False)
+    tmp.close()
+    try:
+        if cfg.family == "hubert":
+            from s3prl.upstream.hubert.expert import UpstreamExpert
+            from s3prl.upstream.hubert.hubert_model import HubertConfig, HubertModel, HubertPretrainingConfig
+            from s3prl.upstream.utils import merge_with_parent
+
+            model_cfg.update(label_rate=50.0, final_dim=256, untie_final_proj=True)
+            task_cfg = dict(normalize=cfg.normalize, sample_rate=16000, label_rate=50.0)
+            symbols = [[str(i) for i in range(504)]]
+            skeleton = HubertModel(
+                merge_with_parent(HubertConfig, model_cfg), merge_with_parent(HubertPretrainingConfig, task_cfg), symbols
+            )
+            full = skeleton.state_dict()
+            full.update(sd)
+            torch.save(
+                {"task_cfg": task_cfg, "model_cfg": model_cfg, "model_weight": full, "dictionaries_symbols": symbols},
+                tmp.name,
+            )
+        elif cfg.family == "wav2vec2":
+            from s3prl.upstream.utils import merge_with_parent
+            from s3prl.upstream.wav2vec2.expert import UpstreamExpert
+            from s3prl.upstream.wav2vec2.wav2vec2_model import Wav2Vec2Config, Wav2Vec2Model
+
+            model_cfg.update(quantize_targets=True, final_dim=768 if cfg.encoder_embed_dim == 1024 else 256)
+            task_cfg = dict(normalize=cfg.normalize, sample_rate=16000)
+            skeleton = Wav2Vec2Model(merge_with_parent(Wav2Vec2Config, model_cfg))
+            full = skeleton.state_dict()
+            full.update(sd)
+            torch.save({"task_cfg": task_cfg, "model_cfg": model_cfg, "model_weight": full}, tmp.name)
+        else:
+            from s3prl.upstream.wavlm.expert import UpstreamExpert
+            from s3prl.upstream.wavlm.WavLM import WavLM, WavLMConfig
+
+            model_cfg.update(
+                normalize=cfg.normalize,
+                relative_position_embedding=True,
+                num_buckets=cfg.num_buckets,
+                max_distance=cfg.max_distance,
+                gru_rel_pos=cfg.gru_rel_pos,
+            )
+            skeleton = WavLM(WavLMConfig(model_cfg))
+            full = skeleton.state_dict()
+            full.update(sd)
+            torch.save({"cfg": model_cfg, "model": full}, tmp.name)
+        missing = set(sd) - set(skeleton.state_dict())
+        assert not missing, f"fabricated keys unknown to the reference model: {sorted(missing)[:5]}"
+        expert = UpstreamExpert(tmp.name)
+    finally:
+        os.unlink(tmp.name)
+    expert.eval()
+    return expert
+
+
+def make_model_fixture(name: str):
+    lens_cases, cstride = CASES[name]
+    sd = fabricate_state_dict(ARCHS[name], seed=0)
+    expert = reference_expert(name, sd)
+    out = {"arch": name, "weight_seed": 0, "channel_stride": cstride, "cases": []}
+    for ci, lens in enumerate(lens_cases):
+        wavs = seeded_wavs(lens, seed=100 + ci)
+        with torch.no_grad():
+            res = expert(wavs)
+        hs = [h.float() for h in res["hidden_states"]]
+        out["cases"].append(
+            {
+                "lens": lens,
+                "wav_seed": 100 + ci,
+                "shape": tuple(hs[0].shape),
+                "num_hidden": len(hs),
+                "sub": torch.stack([h[:, :, ::cstride].contiguous() for h in hs]),
+                "norms": torch.tensor([h.double().norm().item() for h in hs]),
+                "abs_max": torch.tensor([h.abs().max().item() for h in hs]),
+            }
+        )
+        print(f"{name} case {ci}: lens={lens} -> {len(hs)} x {tuple(hs[0].shape)}")
+    torch.save(out, GOLDEN / f"{name}.pt")
+
+
+def make_integer_fixture():
+    """Frame-mask rules, WavLM buckets and length rules straight from the reference code."""
+    from s3prl.upstream.hubert.hubert_model import HubertModel
+    from s3prl.upstream.interfaces import Featurizer  # noqa: F401  (rule restated below, see tolist)
+    from s3prl.upstream.wav2vec2.wav2vec2_model import Wav2Vec2Config, Wav2Vec2Model
+    from s3prl.upstream.wavlm.modules import MultiheadAttention as WavLMAttention
+
+    g = torch.Generator().manual_seed(7)
+    batches = []
+    w2v = Wav2Vec2Model(Wav2Vec2Config(encoder_layers=1, quantize_targets=False))
+    for _ in range(60):
+        B = int(torch.randint(1, 7, (1,), generator=g))
+        lens = torch.randint(400, 170000, (B,), generator=g).tolist()
+        if torch.rand(1, generator=g).item() < 0.3:
+            lens = [max(lens)] * B  # no padding at all
+        Lmax = max(lens)
+        pad = ~torch.lt(torch.arange(Lmax).unsqueeze(0), torch.tensor(lens).unsqueeze(1))
+        n = Lmax
+        for _d, k, s in CONV_LAYERS:
+            n = (n - k) // s + 1
+        T = n
+        feats = torch.zeros(B, T, 1)
+        hub_mask = HubertModel.forward_padding_mask(None, feats, pad)
+        # wav2vec2 rule: replay the statements of Wav2Vec2Model.forward (wav2vec2_model.py:2652-2671)
+        if pad.any():
+            input_lengths = (1 - pad.long()).sum(-1)
+            output_lengths = w2v._get_feat_extract_output_lengths(input_lengths)
+            m = torch.zeros((B, T), dtype=torch.float32)
+            m[(torch.arange(B), output_lengths - 1)] = 1
+            w2v_mask = (1 - m.flip([-1]).cumsum(-1).flip([-1])).bool()
+            w2v_valid = [int((~r).sum()) for r in w2v_mask]
+        else:
+            w2v_valid = [T] * B
+        batches.append(
+            {
+                "lens": lens,
+                "T": T,
+                "hubert_valid": [int((~r).sum()) for r in hub_mask],
+                "hubert_prefix": bool(all((r[: int((~r).sum())] == False).all() for r in hub_mask)),  # noqa: E712
+                "wav2vec2_valid": w2v_valid,
+                "featurizer_len": [round(n_ / 320) for n_ in lens],
+                "s3prl_upstream_len": [(n_ - 1) // 320 + 1 for n_ in lens],
+            }
+        )
+    att = WavLMAttention(768, 12, has_relative_attention_bias=True, num_buckets=320, max_distance=800)
+    rel = torch.arange(-2100, 2101, dtype=torch.long)
+    buckets = att._relative_positions_bucket(rel.unsqueeze(0), bidirectional=True)[0]
+    torch.save({"batches": batches, "wavlm_rel": rel, "wavlm_bucket": buckets}, GOLDEN / "integer_rules.pt")
+    print(f"integer rules: {len(batches)} batches, {len(rel)} relative positions")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    args = ap.parse_args()
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    torch.manual_seed(0)
+    if args.only in (None, "integer"):
+        make_integer_fixture()
+    for name in CASES:
+        if args.only in (None, name):
+            make_model_fixture(name)
+
+
+if __name__ == "__main__":
+    main()

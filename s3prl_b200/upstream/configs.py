@@ -1,0 +1,98 @@
+"""Architecture descriptions of the wav2vec 2.0 / HuBERT / WavLM upstreams served by the B200 path.
+
+Field values are those of the public checkpoints; names follow the reference's
+``HubertConfig`` (s3prl/upstream/hubert/hubert_model.py:76-278), ``Wav2Vec2Config``
+(s3prl/upstream/wav2vec2/wav2vec2_model.py:2103-2350) and ``WavLMConfig`` (s3prl/upstream/wavlm/WavLM.py:162-245).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, replace
+from typing import Dict
+
+CONV_LAYERS = [(512, 10, 5)] + [(512, 3, 2)] * 4 + [(512, 2, 2)] * 2
+DOWNSAMPLE_RATE = 320
+
+
+@dataclass(frozen=True)
+class ArchConfig:
+    family: str  # "hubert" | "wav2vec2" | "wavlm"
+    extractor_mode: str = "default"  # "default" (GroupNorm after conv 0) | "layer_norm"
+    conv_bias: bool = False
+    layer_norm_first: bool = False
+    normalize: bool = False  # task_cfg.normalize: per-utterance waveform layer_norm
+    encoder_layers: int = 12
+    encoder_embed_dim: int = 768
+    encoder_ffn_embed_dim: int = 3072
+    encoder_attention_heads: int = 12
+    conv_pos: int = 128
+    conv_pos_groups: int = 16
+    # WavLM
+    relative_position_embedding: bool = False
+    num_buckets: int = 320
+    max_distance: int = 800
+    gru_rel_pos: bool = False
+
+    @property
+    def family_id(self) -> int:
+        return {"hubert": 0, "wav2vec2": 1, "wavlm": 2}[self.family]
+
+
+_BASE = ArchConfig(family="hubert")
+_LARGE = dict(encoder_layers=24, encoder_embed_dim=1024, encoder_ffn_embed_dim=4096, encoder_attention_heads=16)
+_LL60K = dict(extractor_mode="layer_norm", conv_bias=True, layer_norm_first=True, normalize=True, **_LARGE)
+_WAVLM = dict(family="wavlm", relative_position_embedding=True, gru_rel_pos=True)
+
+ARCHS: Dict[str, ArchConfig] = {
+    # HuBERT (s3prl/upstream/hubert/hubconf.py:85-108)
+    "hubert_base": _BASE,
+    "hubert_large_ll60k": replace(_BASE, **_LL60K),
+    # wav2vec 2.0 (s3prl/upstream/wav2vec2/hubconf.py:83-120)
+    "wav2vec2_base_960": replace(_BASE, family="wav2vec2"),
+    "wav2vec2_large_960": replace(_BASE, family="wav2vec2", **_LARGE),
+    "wav2vec2_large_ll60k": replace(_BASE, family="wav2vec2", **_LL60K),
+    # WavLM (s3prl/upstream/wavlm/hubconf.py:38-78)
+    "wavlm_base": replace(_BASE, **_WAVLM),
+    "wavlm_base_plus": replace(_BASE, **_WAVLM),
+    "wavlm_large": replace(_BASE, **_WAVLM, **_LL60K),
+}
+ALIASES = {
+    "hubert": "hubert_base",
+    "hubert_large": "hubert_large_ll60k",
+    "wav2vec2": "wav2vec2_base_960",
+    "wav2vec2_large": "wav2vec2_large_960",
+    "wavlm": "wavlm_base",
+}
+
+
+def get_arch(name: str) -> ArchConfig:
+    name = ALIASES.get(name, name)
+    if name not in ARCHS:
+        raise KeyError(f"unknown upstream architecture '{name}'; known: {sorted(ARCHS) + sorted(ALIASES)}")
+    return ARCHS[name]
+
+
+def arch_from_reference_cfg(family: str, model_cfg: dict, task_cfg: dict | None = None) -> ArchConfig:
+    """Build an ArchConfig from the ``model_cfg`` / ``task_cfg`` (or WavLM ``cfg``) dict of a converted
+    reference checkpoint (s3prl/upstream/hubert/convert.py:37-56, wavlm/expert.py:37-40)."""
+    g = model_cfg.get
+    normalize = bool((task_cfg or {}).get("normalize", g("normalize", False)))
+    layers = g("conv_feature_layers", None)
+    if layers is not None and list(eval(layers) if isinstance(layers, str) else layers) != CONV_LAYERS:
+        raise ValueError(f"unsupported conv_feature_layers: {layers}")
+    return ArchConfig(
+        family=family,
+        extractor_mode=g("extractor_mode", "default"),
+        conv_bias=bool(g("conv_bias", False)),
+        layer_norm_first=bool(g("layer_norm_first", False)),
+        normalize=normalize,
+        encoder_layers=int(g("encoder_layers", 12)),
+        encoder_embed_dim=int(g("encoder_embed_dim", 768)),
+        encoder_ffn_embed_dim=int(g("encoder_ffn_embed_dim", 3072)),
+        encoder_attention_heads=int(g("encoder_attention_heads", 12)),
+        conv_pos=int(g("conv_pos", 128)),
+        conv_pos_groups=int(g("conv_pos_groups", 16)),
+        relative_position_embedding=bool(g("relative_position_embedding", False)),
+        num_buckets=int(g("num_buckets", 320)),
+        max_distance=int(g("max_distance", 800)),
+        gru_rel_pos=bool(g("gru_rel_pos", False)),
+    )

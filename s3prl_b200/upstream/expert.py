@@ -1,0 +1,224 @@
+"""``UpstreamExpert`` for wav2vec 2.0 / HuBERT / WavLM backed by the sm_100a C-ABI library.
+
+Mirrors the reference interface (s3prl/upstream/hubert/expert.py:26-72, wav2vec2/expert.py:20-97,
+wavlm/expert.py:33-87 and the UpstreamBase result dict, s3prl/upstream/interfaces.py:100-131):
+
+    expert = UpstreamExpert(ckpt=None, name="hubert_base")
+    result = expert([wav_0, wav_1, ...])          # list of 1-D fp32 CUDA tensors, un-padded
+    result["hidden_states"]                        # tuple of NL+1 tensors [B, T, D] (fp32)
+    result["last_hidden_state"], result["hidden_state_{i}"]
+    expert.get_downsample_rates("hidden_states")   # 320
+
+The forward is inference-only (frozen upstream, the configuration SUPERB uses); asking for gradients
+through it raises instead of silently returning constants.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Union
+
+import torch
+import torch.nn as nn
+
+from .. import lib as _lib
+from .configs import DOWNSAMPLE_RATE, ArchConfig, get_arch
+from .weights import fabricate_state_dict, load_reference_checkpoint
+
+SAMPLE_RATE = 16000
+
+
+def _c_config(cfg: ArchConfig) -> _lib.S3BConfig:
+    c = _lib.S3BConfig()
+    c.family = cfg.family_id
+    c.extractor_layer_norm = int(cfg.extractor_mode == "layer_norm")
+    c.conv_bias = int(cfg.conv_bias)
+    c.layer_norm_first = int(cfg.layer_norm_first)
+    c.normalize_wav = int(cfg.normalize)
+    c.num_layers = cfg.encoder_layers
+    c.embed_dim = cfg.encoder_embed_dim
+    c.ffn_dim = cfg.encoder_ffn_embed_dim
+    c.num_heads = cfg.encoder_attention_heads
+    c.pos_conv_kernel = cfg.conv_pos
+    c.pos_conv_groups = cfg.conv_pos_groups
+    c.relative_position = int(cfg.relative_position_embedding)
+    c.num_buckets = cfg.num_buckets
+    c.max_distance = cfg.max_distance
+    c.gru_rel_pos = int(cfg.gru_rel_pos)
+    return c
+
+
+class _NativeModel:
+    """Owner of one ``s3b_model`` handle (weights resident on one CUDA device)."""
+
+    def __init__(self, cfg: ArchConfig, state_dict: Dict[str, torch.Tensor], device: torch.device):
+        self.lib = _lib.load()
+        _lib.require_gpu()
+        self.cfg = cfg
+        self.device = device
+        self.handle = C.c_void_p()
+        cc = _c_config(cfg)
+        _lib.check(self.lib.s3b_model_create(C.byref(cc), C.byref(self.handle)))
+        try:
+            for name, t in state_dict.items():
+                if not torch.is_tensor(t) or not t.is_floating_point():
+                    continue
+                t = t.detach().to("cpu", torch.float32).contiguous()
+                shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
+                _lib.check(
+                    self.lib.s3b_model_set_tensor(self.handle, name.encode(), C.c_void_p(t.data_ptr()), shape, t.dim())
+                )
+            with torch.cuda.device(device):
+                _lib.check(self.lib.s3b_model_finalize(self.handle))
+        except Exception:
+            self.close()
+            raise
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle:
+            self.lib.s3b_model_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class UpstreamExpert(nn.Module):
+    def __init__(
+        self,
+        ckpt: Optional[str] = None,
+        name: str = "hubert_base",
+        model_config: Optional[str] = None,
+        seed: int = 0,
+        state_dict: Optional[Dict[str, torch.Tensor]] = None,
+        arch: Optional[ArchConfig] = None,
+        **kwargs,
+    ):
+        super().__init__()
+        self.name = name
+        family = (arch or get_arch(name)).family if (arch is not None or ckpt is None) else _family_of(name)
+        if ckpt is not None:
+            self.arch, sd = load_reference_checkpoint(ckpt, family)
+        else:
+            self.arch = arch or get_arch(name)
+            sd = state_dict if state_dict is not None else fabricate_state_dict(self.arch, seed)
+        self._state_dict_host = sd  # kept on the host until the first device placement
+        self._native: Optional[_NativeModel] = None
+        self.global_max_len: Optional[int] = None  # set when a batch is sharded across ranks
+        # a buffer so that .to(device) / .cuda() tell us where to live, like any nn.Module
+        self.register_buffer("_device_anchor", torch.zeros(1), persistent=False)
+
+    # ---- nn.Module plumbing ------------------------------------------------------------------------
+    def _ensure_native(self, device: torch.device) -> _NativeModel:
+        if device.type != "cuda":
+            raise _lib.S3BError(
+                "s3prl_b200 runs on CUDA devices only (sm_100a); there is no CPU fallback. "
+                "Move the expert and the waveforms to a B200: expert.to('cuda')."
+            )
+        if self._native is None or self._native.device != device:
+            if self._native is not None:
+                self._native.close()
+            self._native = _NativeModel(self.arch, self._state_dict_host, device)
+        return self._native
+
+    def get_downsample_rates(self, key: str) -> int:
+        return DOWNSAMPLE_RATE
+
+    @property
+    def num_layers(self) -> int:
+        return self.arch.encoder_layers
+
+    @property
+    def hidden_size(self) -> int:
+        return self.arch.encoder_embed_dim
+
+    def num_frames(self, max_len: int) -> int:
+        n = max_len
+        for k, s in ((10, 5), (3, 2), (3, 2), (3, 2), (3, 2), (2, 2), (2, 2)):
+            n = (n - k) // s + 1 if n >= k else 0
+        return n
+
+    def valid_frames(self, lens: List[int], max_len: Optional[int] = None) -> List[int]:
+        """Number of un-padded frames per utterance (the frame padding mask is ``t >= valid_frames[b]``)."""
+        lib = _lib.load()
+        B = len(lens)
+        max_len = max_len or max(lens)
+        arr = (C.c_int64 * B)(*lens)
+        out = (C.c_int32 * B)()
+        native = self._native
+        if native is None:
+            # bookkeeping only needs the config: use a throw-away, un-finalized handle (no GPU work)
+            h = C.c_void_p()
+            cc = _c_config(self.arch)
+            _lib.check(lib.s3b_model_create(C.byref(cc), C.byref(h)))
+            try:
+                _lib.check(lib.s3b_valid_frames(h, arr, B, max_len, out))
+            finally:
+                lib.s3b_model_destroy(h)
+        else:
+            _lib.check(lib.s3b_valid_frames(native.handle, arr, B, max_len, out))
+        return list(out)
+
+    # ---- the hot path ------------------------------------------------------------------------------
+    def forward(self, wavs: List[torch.Tensor]) -> Dict[str, Union[torch.Tensor, tuple]]:
+        if len(wavs) == 0:
+            raise ValueError("empty batch")
+        device = wavs[0].device
+        native = self._ensure_native(device)
+        if any(w.requires_grad for w in wavs):
+            raise _lib.S3BError(
+                "s3prl_b200 upstreams are inference-only (frozen upstream); gradients w.r.t. the waveform "
+                "or upstream weights are not available. Do not pass -f/--upstream_trainable."
+            )
+        wavs = [w.detach().to(torch.float32).contiguous() for w in wavs]
+        lens = [int(w.numel()) for w in wavs]
+        B = len(wavs)
+        max_len = self.global_max_len or max(lens)
+        T = self.num_frames(max_len)
+        if T < 1:
+            raise ValueError(f"waveforms too short ({max_len} samples): the conv stack needs >= 400 samples")
+        NL, D = self.arch.encoder_layers, self.arch.encoder_embed_dim
+        with torch.cuda.device(device):
+            out = torch.empty((NL + 1, B, T, D), dtype=torch.float32, device=device)
+            ptrs = (C.c_void_p * B)(*[w.data_ptr() for w in wavs])
+            lens_c = (C.c_int64 * B)(*lens)
+            _lib.check(
+                native.lib.s3b_forward(
+                    native.handle, ptrs, lens_c, B, max_len, C.c_void_p(out.data_ptr()),
+                    C.c_void_p(torch.cuda.current_stream(device).cuda_stream),
+                )
+            )
+        hidden_states = tuple(out[i] for i in range(NL + 1))
+        result: Dict[str, Union[torch.Tensor, tuple]] = {
+            "_hidden_states_info": tuple([f"self.model.encoder.layers[{i}]" for i in range(NL)] + ["self.model.encoder"]),
+            "hidden_states": hidden_states,
+            "last_hidden_state": hidden_states[-1],
+        }
+        for i, h in enumerate(hidden_states):
+            result[f"hidden_state_{i}"] = h
+        return result
+
+    def forward_host(self, wavs_host: List[torch.Tensor]) -> torch.Tensor:
+        """End-to-end from HOST buffers through ``s3b_forward_host`` (H2D and D2H inside the call).
+        Returns a pinned host tensor [NL+1, B, T, D]."""
+        native = self._ensure_native(self._device_anchor.device)
+        wavs = [w.detach().to("cpu", torch.float32).contiguous() for w in wavs_host]
+        lens = [int(w.numel()) for w in wavs]
+        B = len(wavs)
+        max_len = self.global_max_len or max(lens)
+        T = self.num_frames(max_len)
+        out = torch.empty((self.arch.encoder_layers + 1, B, T, self.arch.encoder_embed_dim), dtype=torch.float32).pin_memory()
+        ptrs = (C.c_void_p * B)(*[w.data_ptr() for w in wavs])
+        lens_c = (C.c_int64 * B)(*lens)
+        with torch.cuda.device(native.device):
+            _lib.check(native.lib.s3b_forward_host(native.handle, ptrs, lens_c, B, max_len, C.c_void_p(out.data_ptr())))
+        return out
+
+
+def _family_of(name: str) -> str:
+    for fam in ("hubert", "wav2vec2", "wavlm"):
+        if name.startswith(fam):
+            return fam
+    raise KeyError(f"cannot infer the model family from '{name}'")

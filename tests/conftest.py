@@ -11,6 +11,7 @@ if str(ROOT) not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with `-m gpu` on the GPU box")
+    config.addinivalue_line("markers", "slow: multi-minute CPU test (24-layer oracles); still part of the default run")
 
 
 @pytest.fixture(scope="session")

@@ -1,0 +1,89 @@
+"""CPU tests pinning the oracle (oracle/upstream_oracle.py) to golden vectors produced by executing the
+reference itself (oracle/make_golden.py -> tests/golden/*.pt). These run without a GPU."""
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT / "oracle"))
+GOLDEN = ROOT / "tests" / "golden"
+
+import upstream_oracle as O  # noqa: E402
+from s3prl_b200.upstream.configs import ARCHS  # noqa: E402
+from s3prl_b200.upstream.weights import fabricate_state_dict  # noqa: E402
+
+MODEL_FIXTURES = sorted(p.stem for p in GOLDEN.glob("*.pt") if p.stem in ARCHS)
+# full-size 24-layer models take a while on CPU; the fast subset keeps the default CPU suite to a few minutes
+FAST = {"hubert_base", "wavlm_base_plus", "wav2vec2_base_960"}
+
+
+def _wavs(lens, seed):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randn(n, generator=g) for n in lens]
+
+
+def test_integer_rules_match_reference():
+    fx = torch.load(GOLDEN / "integer_rules.pt", weights_only=False)
+    for b in fx["batches"]:
+        lens, T = b["lens"], b["T"]
+        assert O.conv_output_length(max(lens)) == T
+        assert O.valid_frames("hubert", lens, max(lens)) == b["hubert_valid"]
+        assert O.valid_frames("wavlm", lens, max(lens)) == b["hubert_valid"]
+        assert O.valid_frames("wav2vec2", lens, max(lens)) == b["wav2vec2_valid"]
+        assert b["hubert_prefix"]
+        assert O.featurizer_lengths(lens) == b["featurizer_len"]
+        assert O.s3prl_upstream_lengths(lens) == b["s3prl_upstream_len"]
+    got = O.wavlm_relative_bucket(fx["wavlm_rel"], 320, 800)
+    assert torch.equal(got, fx["wavlm_bucket"])
+
+
+def test_native_integer_rules_match_reference(s3b_lib):
+    """The C++ bookkeeping of the product (s3b_num_frames / s3b_valid_frames) is integer-exact vs the reference."""
+    from s3prl_b200.upstream.expert import UpstreamExpert
+
+    fx = torch.load(GOLDEN / "integer_rules.pt", weights_only=False)
+    experts = {
+        "hubert": UpstreamExpert(name="hubert_base", state_dict={}),
+        "wav2vec2": UpstreamExpert(name="wav2vec2_base_960", state_dict={}),
+        "wavlm": UpstreamExpert(name="wavlm_base_plus", state_dict={}),
+    }
+    for b in fx["batches"]:
+        lens, T = b["lens"], b["T"]
+        assert experts["hubert"].num_frames(max(lens)) == T
+        assert s3b_lib.s3b_num_frames(None, max(lens)) == T
+        assert experts["hubert"].valid_frames(lens) == b["hubert_valid"]
+        assert experts["wavlm"].valid_frames(lens) == b["hubert_valid"]
+        assert experts["wav2vec2"].valid_frames(lens) == b["wav2vec2_valid"]
+
+
+@pytest.mark.parametrize("name", [n for n in MODEL_FIXTURES if n in FAST])
+def test_oracle_matches_reference_fast(name):
+    _check_model(name)
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("name", [n for n in MODEL_FIXTURES if n not in FAST])
+def test_oracle_matches_reference_large(name):
+    _check_model(name)
+
+
+def _check_model(name):
+    fx = torch.load(GOLDEN / f"{name}.pt", weights_only=False)
+    cfg = ARCHS[name]
+    sd = fabricate_state_dict(cfg, seed=fx["weight_seed"])
+    cs = fx["channel_stride"]
+    for case in fx["cases"]:
+        wavs = _wavs(case["lens"], case["wav_seed"])
+        with torch.no_grad():
+            hs, _pad = O.upstream_forward(wavs, sd, cfg)
+        assert len(hs) == case["num_hidden"]
+        assert tuple(hs[0].shape) == tuple(case["shape"])
+        for l, h in enumerate(hs):
+            ref = case["sub"][l]
+            got = h[:, :, ::cs]
+            rel = ((got.double() - ref.double()).norm() / ref.double().norm()).item()
+            # two fp32 CPU evaluations of the same math (different op order / BLAS blocking)
+            assert rel < 2e-5, (name, l, rel)
+            assert abs(h.double().norm().item() - case["norms"][l].item()) < 2e-5 * case["norms"][l].item()
