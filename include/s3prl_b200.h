@@ -83,6 +83,17 @@ int s3b_forward(s3b_model* m, const float* const* wavs, const int64_t* lens, int
 int s3b_forward_host(s3b_model* m, const float* const* wavs, const int64_t* lens, int32_t batch, int64_t max_len,
                      float* hidden_out);
 
+/* Accounting --------------------------------------------------------------------------------------
+ * Kernel categories: 0 = tcgen05 GEMM, 1 = tcgen05 attention, 2 = conv-0 (+GroupNorm/LayerNorm+GELU),
+ * 3 = LayerNorm kernels, 4 = misc (waveform packing, WavLM gate). With profiling enabled every launch of
+ * s3b_forward is bracketed by CUDA events on the launching stream; s3b_profile_read synchronises the device and
+ * returns, per category, accumulated device milliseconds, ALGORITHMIC flops (2*M*N*K of the un-padded
+ * contraction; 4*T^2*D per utterance and layer for attention) and kernel launches. Arrays have 5 entries. */
+int s3b_profile_enable(s3b_model* m, int32_t enable);
+int s3b_profile_read(s3b_model* m, double* ms, double* flops, int64_t* launches, int32_t reset);
+/* kernels launched by s3b_forward / s3b_forward_host on this model since creation */
+int64_t s3b_launch_count(const s3b_model* m);
+
 /* Featurizer (s3prl/upstream/interfaces.py:217-248) --------------------------------------------------
  * out[i] = sum_l w[l] * hs[l][i], hs = [num][n_per_layer] fp32 device, w = device (already softmaxed). */
 int s3b_weighted_sum(const float* hs, int32_t num, int64_t n_per_layer, const float* w, float* out, void* stream);

@@ -52,6 +52,8 @@ struct GemmParams {
     int T, Tp, H, D;
     float q_scale;
     __nv_bfloat16 *q_hi, *q_lo, *k_hi, *k_lo, *vt_hi, *vt_lo;
+
+    double alg_flops;  // host-side accounting only: 2*M*N*K with the un-padded K
 };
 
 // Launch on `stream`. Returns cudaGetLastError() of the launch.

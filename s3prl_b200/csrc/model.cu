@@ -73,6 +73,7 @@ struct DevBuf {
         if (e != cudaSuccess) return fail("cudaMalloc(%zu) failed: %s", n, cudaGetErrorString(e));
         // zero once so that never-written padding is finite (0 * garbage must not be NaN)
         e = cudaMemset(p, 0, n);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();  // callers may use non-blocking streams
         if (e != cudaSuccess) return fail("cudaMemset failed: %s", cudaGetErrorString(e));
         bytes = n;
         return 0;
@@ -109,11 +110,41 @@ struct LayerW {
     DevBuf grep_w, grep_b, grep_a;  // WavLM gate
 };
 
+// per-category device-time profile (CUDA events around each launch on the launching stream)
+enum { CAT_GEMM = 0, CAT_ATTN = 1, CAT_CONV0 = 2, CAT_NORM = 3, CAT_MISC = 4, CAT_COUNT = 5 };
+struct ProfRec {
+    int cat;
+    cudaEvent_t a, b;
+};
+struct Profiler {
+    bool on = false;
+    std::vector<cudaEvent_t> pool;
+    std::vector<ProfRec> recs;
+    cudaEvent_t pending = nullptr;
+    double ms[CAT_COUNT] = {0, 0, 0, 0, 0};
+    double flops[CAT_COUNT] = {0, 0, 0, 0, 0};
+    long long launches[CAT_COUNT] = {0, 0, 0, 0, 0};
+    cudaEvent_t get() {
+        if (!pool.empty()) {
+            cudaEvent_t e = pool.back();
+            pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+};
+
 struct s3b_model {
     s3b_config cfg;
     std::map<std::string, HostTensor> host;
     bool finalized = false;
     int sm_count = 148;
+    Profiler prof;
+    long long launches_total = 0;  // kernels launched by this model since creation
+    cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+    std::vector<cudaEvent_t> layer_events;
 
     // weights
     DevBuf conv0_w, conv0_b, norm0_g, norm0_b;           // conv 0 (+ GroupNorm or LN affine)
@@ -461,6 +492,7 @@ static int linear_params(GemmParams& p, const __nv_bfloat16* a_hi, const __nv_bf
     p.n_tiles = N / un, p.umma_n = un, p.num_k_blocks = K / 64, p.kb_per_row = K / 64;
     p.a_row_step = 0, p.a_row_off = 0, p.a_k_per_ntile = 0, p.b_n_tiled = 1, p.b_z_per_ntile = 0;
     p.out_rows_per_batch = (int)M;
+    p.alg_flops = 2.0 * (double)M * N * K;
     return 0;
 }
 
@@ -480,6 +512,7 @@ static int conv_params(GemmParams& p, const __nv_bfloat16* a_hi, const __nv_bflo
     p.n_tiles = C / 256, p.umma_n = 256, p.num_k_blocks = K / 64, p.kb_per_row = (2 * C) / 64;
     p.a_row_step = 1, p.a_row_off = 0, p.a_k_per_ntile = 0, p.b_n_tiled = 1, p.b_z_per_ntile = 0, p.b_k_linear = 1;
     p.out_rows_per_batch = (int)Lout;
+    p.alg_flops = 2.0 * (double)B * Lout * C * K;
     return 0;
 }
 
@@ -496,14 +529,48 @@ static int posconv_params(GemmParams& p, const s3b_config& c, const __nv_bfloat1
     p.n_tiles = G, p.umma_n = cpg, p.num_k_blocks = Kp, p.kb_per_row = 1;
     p.a_row_step = 1, p.a_row_off = -(Kp / 2), p.a_k_per_ntile = cpg, p.b_n_tiled = 0, p.b_z_per_ntile = Kp;
     p.out_rows_per_batch = T;
+    p.alg_flops = 2.0 * (double)B * T * D * cpg * Kp;
     return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
+// launch accounting / profiling
+// ------------------------------------------------------------------------------------------------
+static inline void prof_begin(s3b_model* m, cudaStream_t st) {
+    if (!m->prof.on) return;
+    m->prof.pending = m->prof.get();
+    cudaEventRecord(m->prof.pending, st);
+}
+static inline void prof_end(s3b_model* m, cudaStream_t st, int cat, int nkernels, double flops) {
+    m->launches_total += nkernels;
+    if (!m->prof.on) return;
+    cudaEvent_t b = m->prof.get();
+    cudaEventRecord(b, st);
+    m->prof.recs.push_back({cat, m->prof.pending, b});
+    m->prof.launches[cat] += nkernels;
+    m->prof.flops[cat] += flops;
+}
+#define KLAUNCH(cat, nk, fl, expr) \
+    do {                           \
+        prof_begin(m, st);         \
+        CUDA_OK(expr);             \
+        prof_end(m, st, cat, nk, fl); \
+    } while (0)
+#define KGEMM(expr) KLAUNCH(CAT_GEMM, 1, p.alg_flops, expr)
+#define KATTN(expr) KLAUNCH(CAT_ATTN, 1, attn_flops, expr)
+#define KNORM(expr) KLAUNCH(CAT_NORM, 1, 0.0, expr)
+#define KCONV0(nk, expr) KLAUNCH(CAT_CONV0, nk, conv0_flops, expr)
+#define KMISC(expr) KLAUNCH(CAT_MISC, 1, 0.0, expr)
+
+// ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
+// layer_done: optional callback fired (host side) right after hidden state `l` has been enqueued completely
+typedef int (*LayerDoneFn)(s3b_model*, int l, cudaStream_t st, void* user);
+
 static int forward_impl(s3b_model* m, const float* const* wavs_dev, const int64_t* lens, int B, int64_t Lmax,
-                        float* hidden_out, cudaStream_t st) {
+                        float* hidden_out, cudaStream_t st, LayerDoneFn layer_done = nullptr,
+                        void* user = nullptr) {
     const s3b_config& c = m->cfg;
     const int D = c.embed_dim, F = c.ffn_dim, H = c.num_heads, NL = c.num_layers, C = kConvDim;
     if (B < 1) return fail("empty batch");
@@ -518,6 +585,8 @@ static int forward_impl(s3b_model* m, const float* const* wavs_dev, const int64_
     const int T = (int)T64;
     const int64_t M = (int64_t)B * T;
     const int Tp = (T + 7) & ~7;
+    const double attn_flops = 4.0 * (double)T * T * D * B;
+    const double conv0_flops = 2.0 * kConvK[0] * C * (double)B * L[0];
 
     // ---- host-side integer bookkeeping -> device -------------------------------------------------------
     m->kv_host.resize(B);
@@ -556,17 +625,17 @@ static int forward_impl(s3b_model* m, const float* const* wavs_dev, const int64_
     S3B_OK(m->h_s.ensure((size_t)M * F));
 
     // ---- waveform packing (+ normalisation) ------------------------------------------------------------
-    CUDA_OK(launch_wav_pack(m->wav_ptrs.as<const float*>(), m->lens_dev.as<long long>(), B, Lmax, c.normalize_wav,
+    KMISC(launch_wav_pack(m->wav_ptrs.as<const float*>(), m->lens_dev.as<long long>(), B, Lmax, c.normalize_wav,
                             m->wav_stats.as<float>(), m->wav_pad.as<float>(), st));
 
     // ---- conv 0 + norm + GELU -> act[0] (bf16 hi/lo, channels-last) -----------------------------------------
     if (c.extractor_layer_norm) {
-        CUDA_OK(launch_conv0_layernorm(m->wav_pad.as<float>(), B, Lmax, (int)L[0], m->conv0_w.as<float>(),
+        KCONV0(1, launch_conv0_layernorm(m->wav_pad.as<float>(), B, Lmax, (int)L[0], m->conv0_w.as<float>(),
                                        c.conv_bias ? m->conv0_b.as<float>() : nullptr, m->norm0_g.as<float>(),
                                        m->norm0_b.as<float>(), m->act[0].h(), m->act[0].l(), st));
     } else {
         if (c.conv_bias) return fail("conv_bias with extractor_mode=default is not supported");
-        CUDA_OK(launch_conv0_groupnorm(m->wav_pad.as<float>(), B, Lmax, (int)L[0], m->conv0_w.as<float>(),
+        KCONV0(3, launch_conv0_groupnorm(m->wav_pad.as<float>(), B, Lmax, (int)L[0], m->conv0_w.as<float>(),
                                        m->norm0_g.as<float>(), m->norm0_b.as<float>(), m->c0_part.as<float>(),
                                        m->c0_ss.as<float>(), m->act[0].h(), m->act[0].l(), st));
     }
@@ -587,17 +656,17 @@ static int forward_impl(s3b_model* m, const float* const* wavs_dev, const int64_
             else e.out_hi = m->act[i].h(), e.out_lo = m->act[i].l();
         }
         set_epi(p, e, C);
-        CUDA_OK(launch_gemm_bf16x3(p, m->sm_count, st));
+        KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
         if (c.extractor_layer_norm) {
             // per-frame LayerNorm(512) + GELU (wav2vec2_model.py:2887-2897)
-            CUDA_OK(launch_layernorm(m->conv_f32.as<float>(), (size_t)B * L[i], C, m->conv_ln_g[i].as<float>(),
+            KNORM(launch_layernorm(m->conv_f32.as<float>(), (size_t)B * L[i], C, m->conv_ln_g[i].as<float>(),
                                      m->conv_ln_b[i].as<float>(), 1, last ? m->conv_f32.as<float>() : nullptr,
                                      last ? nullptr : m->act[i].h(), last ? nullptr : m->act[i].l(), st));
         }
     }
 
     // ---- LayerNorm(512) -> post_extract_proj (+ zero padded frames) ------------------------------------------
-    CUDA_OK(launch_layernorm(m->conv_f32.as<float>(), (size_t)M, C, m->ln512_g.as<float>(), m->ln512_b.as<float>(), 0,
+    KNORM(launch_layernorm(m->conv_f32.as<float>(), (size_t)M, C, m->ln512_g.as<float>(), m->ln512_b.as<float>(), 0,
                              nullptr, m->ln512_s.h(), m->ln512_s.l(), st));
     {
         S3B_OK(linear_params(p, m->ln512_s.h(), m->ln512_s.l(), m->proj_w.h(), m->proj_w.l(), M, D, C));
@@ -607,7 +676,7 @@ static int forward_impl(s3b_model* m, const float* const* wavs_dev, const int64_
         e.out_f32 = m->x_f32.as<float>();
         e.out_hi = m->x_s.h(), e.out_lo = m->x_s.l();
         set_epi(p, e, D);
-        CUDA_OK(launch_gemm_bf16x3(p, m->sm_count, st));
+        KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
     }
 
     // ---- x = x + GELU(pos_conv(x)) ; post-LN models: LayerNorm -> hidden state 0 ------------------------------
@@ -621,10 +690,11 @@ static int forward_impl(s3b_model* m, const float* const* wavs_dev, const int64_
         e.residual = m->x_f32.as<float>();
         e.out_f32 = c.layer_norm_first ? hs0 : m->tmp_f32.as<float>();
         set_epi(p, e, D);
-        CUDA_OK(launch_gemm_bf16x3(p, m->sm_count, st));
+        KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
         if (!c.layer_norm_first)
-            CUDA_OK(launch_layernorm(m->tmp_f32.as<float>(), (size_t)M, D, m->enc_ln_g.as<float>(),
+            KNORM(launch_layernorm(m->tmp_f32.as<float>(), (size_t)M, D, m->enc_ln_g.as<float>(),
                                      m->enc_ln_b.as<float>(), 0, hs0, m->xs_s.h(), m->xs_s.l(), st));
+        if (layer_done) S3B_OK(layer_done(m, 0, st, user));
     }
 
     // ---- WavLM relative position table (ungated, shared by all layers; WavLM.py:622-632) -----------------------
@@ -633,7 +703,7 @@ static int forward_impl(s3b_model* m, const float* const* wavs_dev, const int64_
         S3B_OK(m->rel_table.ensure((size_t)H * (2 * T - 1) * 4));
         S3B_OK(m->gate.ensure((size_t)B * H * T * 4));
         if (m->rel_table_T != T) {
-            CUDA_OK(launch_wavlm_rel_table(m->rel_table_src.as<float>(), c.num_buckets, c.max_distance, H, T,
+            KMISC(launch_wavlm_rel_table(m->rel_table_src.as<float>(), c.num_buckets, c.max_distance, H, T,
                                            m->rel_table.as<float>(), st));
             m->rel_table_T = T;
         }
@@ -647,7 +717,7 @@ static int forward_impl(s3b_model* m, const float* const* wavs_dev, const int64_
         const bool last = (l == NL - 1);
 
         if (c.layer_norm_first)  // xs = LN1(residual stream)
-            CUDA_OK(launch_layernorm(hs_in, (size_t)M, D, W.ln1_g.as<float>(), W.ln1_b.as<float>(), 0, nullptr,
+            KNORM(launch_layernorm(hs_in, (size_t)M, D, W.ln1_g.as<float>(), W.ln1_b.as<float>(), 0, nullptr,
                                      m->xs_s.h(), m->xs_s.l(), st));
         // QKV projection, scattered per head; q pre-scaled by head_dim^-0.5 (exact power of two)
         S3B_OK(linear_params(p, m->xs_s.h(), m->xs_s.l(), W.qkv.h(), W.qkv.l(), M, 3 * D, D));
@@ -659,7 +729,7 @@ static int forward_impl(s3b_model* m, const float* const* wavs_dev, const int64_
             p.q_hi = m->q_s.h(), p.q_lo = m->q_s.l(), p.k_hi = m->k_s.h(), p.k_lo = m->k_s.l();
             p.vt_hi = m->vt_s.h(), p.vt_lo = m->vt_s.l();
         }
-        CUDA_OK(launch_gemm_bf16x3(p, m->sm_count, st));
+        KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
 
         AttnParams ap;
         memset(&ap, 0, sizeof(ap));
@@ -675,13 +745,13 @@ static int forward_impl(s3b_model* m, const float* const* wavs_dev, const int64_
         if (rel) {
             ap.bias_table = m->rel_table.as<float>();
             // gate from the layer's attention input (post-LN: hs_in; pre-LN: LN1 output) wavlm/modules.py:534-551
-            CUDA_OK(launch_wavlm_gate(m->xs_s.h(), m->xs_s.l(), (size_t)M, B, T, H, D,
+            KMISC(launch_wavlm_gate(m->xs_s.h(), m->xs_s.l(), (size_t)M, B, T, H, D,
                                       c.gru_rel_pos ? W.grep_w.as<float>() : nullptr, W.grep_b.as<float>(),
                                       W.grep_a.as<float>(), m->gate.as<float>(), st));
             ap.gate = m->gate.as<float>();
         }
         ap.ctx_hi = m->ctx_s.h(), ap.ctx_lo = m->ctx_s.l();
-        CUDA_OK(launch_attention(ap, st));
+        KATTN(launch_attention(ap, st));
 
         // out_proj + residual
         S3B_OK(linear_params(p, m->ctx_s.h(), m->ctx_s.l(), W.out.h(), W.out.l(), M, D, D));
@@ -692,12 +762,12 @@ static int forward_impl(s3b_model* m, const float* const* wavs_dev, const int64_
             e.out_f32 = c.layer_norm_first ? m->x1_f32.as<float>() : m->tmp_f32.as<float>();
             set_epi(p, e, D);
         }
-        CUDA_OK(launch_gemm_bf16x3(p, m->sm_count, st));
+        KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
         if (c.layer_norm_first)  // x1_s = LN2(r1), r1 = x1_f32
-            CUDA_OK(launch_layernorm(m->x1_f32.as<float>(), (size_t)M, D, W.ln2_g.as<float>(), W.ln2_b.as<float>(), 0,
+            KNORM(launch_layernorm(m->x1_f32.as<float>(), (size_t)M, D, W.ln2_g.as<float>(), W.ln2_b.as<float>(), 0,
                                      nullptr, m->x1_s.h(), m->x1_s.l(), st));
         else  // x1 = LN1(x + attn)
-            CUDA_OK(launch_layernorm(m->tmp_f32.as<float>(), (size_t)M, D, W.ln1_g.as<float>(), W.ln1_b.as<float>(), 0,
+            KNORM(launch_layernorm(m->tmp_f32.as<float>(), (size_t)M, D, W.ln1_g.as<float>(), W.ln1_b.as<float>(), 0,
                                      m->x1_f32.as<float>(), m->x1_s.h(), m->x1_s.l(), st));
         // fc1 + GELU
         S3B_OK(linear_params(p, m->x1_s.h(), m->x1_s.l(), W.fc1.h(), W.fc1.l(), M, F, D));
@@ -708,7 +778,7 @@ static int forward_impl(s3b_model* m, const float* const* wavs_dev, const int64_
             e.out_hi = m->h_s.h(), e.out_lo = m->h_s.l();
             set_epi(p, e, F);
         }
-        CUDA_OK(launch_gemm_bf16x3(p, m->sm_count, st));
+        KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
         // fc2 + residual
         S3B_OK(linear_params(p, m->h_s.h(), m->h_s.l(), W.fc2.h(), W.fc2.l(), M, D, F));
         {
@@ -719,15 +789,16 @@ static int forward_impl(s3b_model* m, const float* const* wavs_dev, const int64_
             e.out_f32 = (c.layer_norm_first && !last) ? hs_out : m->tmp_f32.as<float>();
             set_epi(p, e, D);
         }
-        CUDA_OK(launch_gemm_bf16x3(p, m->sm_count, st));
+        KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
         if (c.layer_norm_first) {
             if (last)  // encoder.layer_norm on the final output (wav2vec2_model.py:3049-3050)
-                CUDA_OK(launch_layernorm(m->tmp_f32.as<float>(), (size_t)M, D, m->enc_ln_g.as<float>(),
+                KNORM(launch_layernorm(m->tmp_f32.as<float>(), (size_t)M, D, m->enc_ln_g.as<float>(),
                                          m->enc_ln_b.as<float>(), 0, hs_out, nullptr, nullptr, st));
         } else {
-            CUDA_OK(launch_layernorm(m->tmp_f32.as<float>(), (size_t)M, D, W.ln2_g.as<float>(), W.ln2_b.as<float>(), 0,
+            KNORM(launch_layernorm(m->tmp_f32.as<float>(), (size_t)M, D, W.ln2_g.as<float>(), W.ln2_b.as<float>(), 0,
                                      hs_out, last ? nullptr : m->xs_s.h(), last ? nullptr : m->xs_s.l(), st));
         }
+        if (layer_done) S3B_OK(layer_done(m, l + 1, st, user));
     }
     return 0;
 }
@@ -750,19 +821,69 @@ extern "C" int s3b_forward_host(s3b_model* m, const float* const* wavs, const in
     S3B_OK(m->stage_wav.ensure(total * 4));
     const size_t out_elems = (size_t)(m->cfg.num_layers + 1) * batch * T * m->cfg.embed_dim;
     S3B_OK(m->stage_out.ensure(out_elems * 4));
+    if (m->copy_stream == nullptr) CUDA_OK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    if (m->compute_stream == nullptr) CUDA_OK(cudaStreamCreateWithFlags(&m->compute_stream, cudaStreamNonBlocking));
+    while ((int)m->layer_events.size() < m->cfg.num_layers + 1) {
+        cudaEvent_t e;
+        CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        m->layer_events.push_back(e);
+    }
+    cudaStream_t st = m->compute_stream;
     std::vector<const float*> ptrs(batch);
     size_t off = 0;
     for (int b = 0; b < batch; ++b) {
         float* d = m->stage_wav.as<float>() + off;
-        CUDA_OK(cudaMemcpyAsync(d, wavs[b], (size_t)lens[b] * 4, cudaMemcpyHostToDevice, 0));
+        CUDA_OK(cudaMemcpyAsync(d, wavs[b], (size_t)lens[b] * 4, cudaMemcpyHostToDevice, st));
         ptrs[b] = d;
         off += (size_t)lens[b];
     }
-    S3B_OK(forward_impl(m, ptrs.data(), lens, batch, max_len, m->stage_out.as<float>(), 0));
-    CUDA_OK(cudaMemcpyAsync(hidden_out, m->stage_out.p, out_elems * 4, cudaMemcpyDeviceToHost, 0));
-    CUDA_OK(cudaStreamSynchronize(0));
+    // device->host copy of hidden state l overlaps the computation of layer l+1 (second stream)
+    struct Ctx {
+        float* host;
+        size_t per_layer;
+    } ctx{hidden_out, (size_t)batch * T * m->cfg.embed_dim};
+    auto layer_done = [](s3b_model* mm, int l, cudaStream_t s, void* user) -> int {
+        Ctx* c = static_cast<Ctx*>(user);
+        CUDA_OK(cudaEventRecord(mm->layer_events[l], s));
+        CUDA_OK(cudaStreamWaitEvent(mm->copy_stream, mm->layer_events[l], 0));
+        CUDA_OK(cudaMemcpyAsync(c->host + (size_t)l * c->per_layer, mm->stage_out.as<float>() + (size_t)l * c->per_layer,
+                                c->per_layer * 4, cudaMemcpyDeviceToHost, mm->copy_stream));
+        return 0;
+    };
+    S3B_OK(forward_impl(m, ptrs.data(), lens, batch, max_len, m->stage_out.as<float>(), st, layer_done, &ctx));
+    CUDA_OK(cudaStreamSynchronize(st));
+    CUDA_OK(cudaStreamSynchronize(m->copy_stream));
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// profiling / accounting
+// ------------------------------------------------------------------------------------------------
+extern "C" int s3b_profile_enable(s3b_model* m, int32_t enable) {
+    if (!m) return fail("null model");
+    m->prof.on = enable != 0;
+    return 0;
+}
+
+extern "C" int s3b_profile_read(s3b_model* m, double* ms, double* flops, int64_t* launches, int32_t reset) {
+    if (!m || !ms || !flops || !launches) return fail("null argument");
+    CUDA_OK(cudaDeviceSynchronize());
+    for (ProfRec& r : m->prof.recs) {
+        float t = 0.f;
+        CUDA_OK(cudaEventElapsedTime(&t, r.a, r.b));
+        m->prof.ms[r.cat] += t;
+        m->prof.pool.push_back(r.a);
+        m->prof.pool.push_back(r.b);
+    }
+    m->prof.recs.clear();
+    for (int c = 0; c < CAT_COUNT; ++c) {
+        ms[c] = m->prof.ms[c], flops[c] = m->prof.flops[c], launches[c] = m->prof.launches[c];
+        if (reset) m->prof.ms[c] = 0, m->prof.flops[c] = 0, m->prof.launches[c] = 0;
+    }
+    return 0;
+}
+
+extern "C" int64_t s3b_launch_count(const s3b_model* m) { return m ? m->launches_total : -1; }
 
 // ------------------------------------------------------------------------------------------------
 // Featurizer

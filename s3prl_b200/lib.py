@@ -24,6 +24,9 @@ EXPORTED_SYMBOLS = [
     "s3b_valid_frames",
     "s3b_forward",
     "s3b_forward_host",
+    "s3b_profile_enable",
+    "s3b_profile_read",
+    "s3b_launch_count",
     "s3b_weighted_sum",
     "s3b_weighted_sum_backward",
     "s3b_linear_f32",
@@ -93,6 +96,10 @@ def load() -> C.CDLL:
     lib.s3b_valid_frames.argtypes = [vp, C.POINTER(i64), i32, i64, C.POINTER(i32)]
     lib.s3b_forward.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i32, i64, f32p, vp]
     lib.s3b_forward_host.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i32, i64, f32p]
+    lib.s3b_profile_enable.argtypes = [vp, i32]
+    lib.s3b_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64), i32]
+    lib.s3b_launch_count.argtypes = [vp]
+    lib.s3b_launch_count.restype = i64
     lib.s3b_weighted_sum.argtypes = [f32p, i32, i64, f32p, f32p, vp]
     lib.s3b_weighted_sum_backward.argtypes = [f32p, i32, i64, f32p, f32p, vp]
     lib.s3b_linear_f32.argtypes = [f32p, f32p, f32p, f32p, i64, i32, i32, i32, f32p, vp]

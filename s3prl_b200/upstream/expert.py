@@ -209,7 +209,12 @@ class UpstreamExpert(nn.Module):
         B = len(wavs)
         max_len = self.global_max_len or max(lens)
         T = self.num_frames(max_len)
-        out = torch.empty((self.arch.encoder_layers + 1, B, T, self.arch.encoder_embed_dim), dtype=torch.float32).pin_memory()
+        shape = (self.arch.encoder_layers + 1, B, T, self.arch.encoder_embed_dim)
+        out = getattr(self, "_host_out", None)
+        if out is None or tuple(out.shape) != shape:
+            # pinned result buffer, reused across calls of the same shape (valid until the next forward_host)
+            out = torch.empty(shape, dtype=torch.float32).pin_memory()
+            self._host_out = out
         ptrs = (C.c_void_p * B)(*[w.data_ptr() for w in wavs])
         lens_c = (C.c_int64 * B)(*lens)
         with torch.cuda.device(native.device):
