@@ -101,6 +101,13 @@ int s3b_weighted_sum(const float* hs, int32_t num, int64_t n_per_layer, const fl
 int s3b_weighted_sum_backward(const float* hs, int32_t num, int64_t n_per_layer, const float* grad_out,
                               float* grad_w, void* stream);
 
+/* fbank baseline upstream (s3prl/upstream/baseline/expert.py:69-79 over torchaudio.compliance.kaldi.fbank,
+ * fbank.yaml: 80 mel bins, 25 ms / 10 ms, log; + 2 x ComputeDeltas(5) + per-utterance CMVN).
+ *  wavs : host array of `batch` DEVICE pointers (fp32, un-padded), lens : host array of lengths
+ *  out  : DEVICE buffer [batch][s3b_fbank_num_frames(max(lens))][240] fp32, zero beyond each utterance's frames */
+int64_t s3b_fbank_num_frames(int64_t len);
+int s3b_fbank(const float* const* wavs, const int64_t* lens, int32_t batch, float* out, void* stream);
+
 /* Building blocks exposed for parity tests (device pointers, fp32) -------------------------------------- */
 /* out[M][N] = act(A[M][K] * W[N][K]^T + bias[N]) (+ residual[M][N]); K % 64 == 0, N % 16 == 0 */
 int s3b_linear_f32(const float* a, const float* w, const float* bias, const float* residual, int64_t m, int32_t n,

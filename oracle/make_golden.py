@@ -197,6 +197,23 @@ def make_integer_fixture():
     print(f"integer rules: {len(batches)} batches, {len(rel)} relative positions")
 
 
+def make_fbank_fixture():
+    """s3prl.upstream.baseline fbank (config 1: 4 x 1 s, seed 0) + a ragged batch."""
+    from s3prl.upstream.baseline.hubconf import fbank
+
+    expert = fbank()
+    expert.eval()
+    out = {"cases": []}
+    torch.manual_seed(0)
+    c1 = [torch.randn(16000) for _ in range(4)]  # BASELINE.md C1
+    for name, wavs in (("c1_4x1s_seed0", c1), ("ragged", seeded_wavs([16000, 9999, 4000, 480], 321))):
+        with torch.no_grad():
+            hs = expert(wavs)["hidden_states"][0]
+        out["cases"].append({"name": name, "lens": [len(w) for w in wavs], "out": hs.float().clone()})
+        print(f"fbank {name}: {tuple(hs.shape)}")
+    torch.save(out, GOLDEN / "fbank.pt")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -205,6 +222,8 @@ def main():
     torch.manual_seed(0)
     if args.only in (None, "integer"):
         make_integer_fixture()
+    if args.only in (None, "fbank"):
+        make_fbank_fixture()
     for name in CASES:
         if args.only in (None, name):
             make_model_fixture(name)

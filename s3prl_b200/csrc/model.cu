@@ -979,3 +979,30 @@ extern "C" int s3b_attention_f32(const float* q, const float* k, const float* v,
     if (se != cudaSuccess) return fail("attention execution failed: %s", cudaGetErrorString(se));
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// fbank baseline (s3prl/upstream/baseline/expert.py:69-79)
+// ------------------------------------------------------------------------------------------------
+#include "fbank.cuh"
+
+extern "C" int64_t s3b_fbank_num_frames(int64_t len) { return len < 400 ? 0 : 1 + (len - 400) / 160; }
+
+extern "C" int s3b_fbank(const float* const* wavs, const int64_t* lens, int32_t batch, float* out, void* stream) {
+    if (!wavs || !lens || !out) return fail("null argument");
+    if (batch < 1) return fail("empty batch");
+    if (s3b_device_count() == 0) return fail("no CUDA device: s3prl_b200 has no CPU fallback");
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t max_len = 0;
+    for (int b = 0; b < batch; ++b) max_len = lens[b] > max_len ? lens[b] : max_len;
+    const int64_t max_frames = s3b_fbank_num_frames(max_len);
+    if (max_frames < 1) return fail("waveforms shorter than one 25 ms frame");
+    static thread_local DevBuf scratch;
+    S3B_OK(scratch.ensure((size_t)batch * (sizeof(void*) + sizeof(long long))));
+    std::vector<long long> l64(lens, lens + batch);
+    const float** d_ptrs = scratch.as<const float*>();
+    long long* d_lens = reinterpret_cast<long long*>(scratch.as<char>() + (size_t)batch * sizeof(void*));
+    CUDA_OK(cudaMemcpyAsync(d_ptrs, wavs, batch * sizeof(void*), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(d_lens, l64.data(), batch * sizeof(long long), cudaMemcpyHostToDevice, st));
+    CUDA_OK(launch_fbank(d_ptrs, d_lens, batch, (int)max_frames, out, st));
+    return 0;
+}

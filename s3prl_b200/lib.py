@@ -32,6 +32,8 @@ EXPORTED_SYMBOLS = [
     "s3b_linear_f32",
     "s3b_layernorm_f32",
     "s3b_attention_f32",
+    "s3b_fbank",
+    "s3b_fbank_num_frames",
 ]
 
 
@@ -105,6 +107,9 @@ def load() -> C.CDLL:
     lib.s3b_linear_f32.argtypes = [f32p, f32p, f32p, f32p, i64, i32, i32, i32, f32p, vp]
     lib.s3b_layernorm_f32.argtypes = [f32p, i64, i32, f32p, f32p, i32, f32p, vp]
     lib.s3b_attention_f32.argtypes = [f32p, f32p, f32p, C.POINTER(i32), i32, i32, i32, f32p, vp]
+    lib.s3b_fbank_num_frames.argtypes = [i64]
+    lib.s3b_fbank_num_frames.restype = i64
+    lib.s3b_fbank.argtypes = [C.POINTER(vp), C.POINTER(i64), i32, f32p, vp]
     _lib = lib
     return lib
 

@@ -1,0 +1,111 @@
+"""Launcher: the reference's ``run_downstream.py`` with the B200-native upstreams injected into ``s3prl.hub``.
+
+    python -m s3prl_b200.run_downstream -m train -u hubert_base -d ctc -c downstream/ctc/librispeech.yaml -n exp
+
+is ``python run_downstream.py ...`` of the reference (s3prl/run_downstream.py:153-215) except that, before its
+``main()`` runs, (1) stub modules are registered for optional third-party imports that this image lacks and that the
+upstream path never touches, and (2) ``s3prl_b200.hub.install(s3prl.hub)`` replaces the hub entries
+(``Runner._get_upstream`` does ``getattr(hub, args.upstream)``, s3prl/downstream/runner.py:141). The reference tree
+is not modified; it only has to be importable (``pip install s3prl`` or ``PYTHONPATH=/path/to/s3prl``).
+"""
+from __future__ import annotations
+
+import importlib
+import sys
+import types
+
+
+def _stub(name: str, **attrs) -> types.ModuleType:
+    mod = types.ModuleType(name)
+    mod.__dict__.update(attrs)
+    mod.__s3prl_b200_stub__ = True
+    sys.modules[name] = mod
+    return mod
+
+
+def _have(name: str) -> bool:
+    try:
+        importlib.import_module(name)
+        return True
+    except Exception:
+        return False
+
+
+def install_shims() -> list:
+    """Register no-op stand-ins for imports the reference performs at module import time but that are absent or
+    removed in this environment. Returns the names that were stubbed. None of them is used on the upstream path."""
+    stubbed = []
+    import torchaudio
+
+    if not hasattr(torchaudio, "set_audio_backend"):  # removed in torchaudio >= 2.2 (run_downstream.py:157)
+        torchaudio.set_audio_backend = lambda *a, **k: None
+        stubbed.append("torchaudio.set_audio_backend")
+    if not _have("torchaudio.sox_effects"):
+        _stub("torchaudio.sox_effects", apply_effects_tensor=None, apply_effects_file=None)
+        stubbed.append("torchaudio.sox_effects")
+    if not _have("omegaconf"):
+        class _Missing:  # noqa: N801
+            def __init__(self, *a, **k):
+                raise ImportError("omegaconf is not installed (only needed by data2vec / fairseq converters)")
+
+        _stub("omegaconf", OmegaConf=_Missing, DictConfig=dict, II=lambda x: x, MISSING="???", open_dict=None,
+              is_primitive_type=lambda *_: True)
+        stubbed.append("omegaconf")
+    if not _have("tensorboardX"):
+        class SummaryWriter:  # minimal logger used by Runner (runner.py:267-268)
+            def __init__(self, *a, **k):
+                pass
+
+            def add_scalar(self, *a, **k):
+                pass
+
+            def close(self):
+                pass
+
+        _stub("tensorboardX", SummaryWriter=SummaryWriter)
+        stubbed.append("tensorboardX")
+    if not _have("editdistance"):
+        def _eval(a, b):
+            prev = list(range(len(b) + 1))
+            for i, x in enumerate(a, 1):
+                cur = [i]
+                for j, y in enumerate(b, 1):
+                    cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (x != y)))
+                prev = cur
+            return prev[-1]
+
+        _stub("editdistance", eval=_eval)
+        stubbed.append("editdistance")
+    try:
+        import huggingface_hub
+
+        for missing in ("HfFolder", "Repository"):  # removed in recent huggingface_hub (runner.py:27)
+            if not hasattr(huggingface_hub, missing):
+                setattr(huggingface_hub, missing, type(missing, (), {}))
+                stubbed.append(f"huggingface_hub.{missing}")
+    except Exception:
+        _stub("huggingface_hub", HfApi=object, HfFolder=object, Repository=object)
+        stubbed.append("huggingface_hub")
+    return stubbed
+
+
+def inject() -> list:
+    """Import ``s3prl.hub`` (with shims) and replace its wav2vec2 / HuBERT / WavLM / fbank entries."""
+    install_shims()
+    import s3prl.hub as ref_hub
+
+    from . import hub as our_hub
+
+    return our_hub.install(ref_hub)
+
+
+def main():
+    names = inject()
+    print(f"[s3prl_b200] injected {len(names)} B200-native entries into s3prl.hub", file=sys.stderr)
+    from s3prl import run_downstream
+
+    run_downstream.main()
+
+
+if __name__ == "__main__":
+    main()

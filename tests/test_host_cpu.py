@@ -1,0 +1,136 @@
+"""CPU tests of the host-side logic: C-ABI symbol export, loud failure without a GPU, hub injection into the
+reference (when /root/reference is present), utterance sharding + gather over gloo with world_size 2."""
+import os
+import re
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+REFERENCE = Path("/root/reference")
+
+
+def test_cabi_exports_every_declared_symbol(s3b_lib):
+    from s3prl_b200 import lib
+
+    header = (ROOT / "include" / "s3prl_b200.h").read_text()
+    declared = set(re.findall(r"\b(s3b_[a-z0-9_]+)\s*\(", header))
+    declared -= {"s3b_model", "s3b_config"}
+    assert declared, "no declarations parsed"
+    for sym in sorted(declared):
+        assert hasattr(s3b_lib, sym), f"{sym} declared in include/s3prl_b200.h but not exported"
+    assert declared == set(lib.EXPORTED_SYMBOLS)
+    assert s3b_lib.s3b_version() >= 100
+    assert s3b_lib.s3b_fbank_num_frames(16000) == 98
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the GPU-less behaviour")
+def test_no_cpu_fallback(s3b_lib):
+    from s3prl_b200 import lib
+    from s3prl_b200.hub import fbank
+    from s3prl_b200.upstream.expert import UpstreamExpert
+
+    assert s3b_lib.s3b_device_count() == 0
+    expert = UpstreamExpert(name="hubert_base", state_dict={})
+    with pytest.raises(lib.S3BError):
+        expert([torch.randn(16000)])
+    with pytest.raises(lib.S3BError):
+        fbank()([torch.randn(16000)])
+
+
+def test_config_from_reference_cfg_dict():
+    from s3prl_b200.upstream.configs import ARCHS, arch_from_reference_cfg
+
+    cfg = arch_from_reference_cfg(
+        "wav2vec2",
+        dict(extractor_mode="layer_norm", conv_bias=True, layer_norm_first=True, encoder_layers=24,
+             encoder_embed_dim=1024, encoder_ffn_embed_dim=4096, encoder_attention_heads=16,
+             conv_feature_layers="[(512, 10, 5)] + [(512, 3, 2)] * 4 + [(512,2,2)] + [(512,2,2)]"),
+        dict(normalize=True),
+    )
+    assert cfg == ARCHS["wav2vec2_large_ll60k"]
+    with pytest.raises(ValueError):
+        arch_from_reference_cfg("hubert", dict(conv_feature_layers="[(512, 10, 5)]"))
+
+
+def test_fabricated_state_dict_is_deterministic_and_loadable_layout():
+    from s3prl_b200.upstream.configs import ARCHS
+    from s3prl_b200.upstream.weights import fabricate_state_dict
+
+    a = fabricate_state_dict(ARCHS["wavlm_base_plus"], 0)
+    b = fabricate_state_dict(ARCHS["wavlm_base_plus"], 0)
+    assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+    assert a["encoder.pos_conv.0.weight_v"].shape == (768, 48, 128)
+    assert a["encoder.layers.0.self_attn.relative_attention_bias.weight"].shape == (320, 12)
+    assert a["feature_extractor.conv_layers.0.2.weight"].shape == (512,)
+    c = fabricate_state_dict(ARCHS["wav2vec2_large_ll60k"], 0)
+    assert c["feature_extractor.conv_layers.3.2.1.weight"].shape == (512,)
+    assert c["feature_extractor.conv_layers.3.0.bias"].shape == (512,)
+
+
+@pytest.mark.skipif(not REFERENCE.exists(), reason="reference tree not present (GPU box)")
+def test_hub_injection_into_reference():
+    """`getattr(s3prl.hub, name)` — what Runner._get_upstream does (runner.py:141) — yields our expert."""
+    import subprocess
+
+    code = (
+        "from s3prl_b200 import run_downstream as R\n"
+        "names = R.inject()\n"
+        "import s3prl.hub as hub\n"
+        "from s3prl_b200.upstream.expert import UpstreamExpert\n"
+        "from s3prl_b200.upstream.baseline import FbankExpert\n"
+        "e = getattr(hub, 'hubert_base')(ckpt=None, model_config=None, refresh=False)\n"
+        "assert isinstance(e, UpstreamExpert) and e.get_downsample_rates('hidden_states') == 320\n"
+        "assert isinstance(hub.fbank(), FbankExpert)\n"
+        "assert isinstance(hub.wavlm_base_plus(), UpstreamExpert)\n"
+        "from s3prl.downstream.runner import Runner\n"
+        "print('OK', len(names))\n"
+    )
+    env = dict(os.environ, PYTHONPATH=f"{REFERENCE}:{ROOT}")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp", timeout=600)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
+
+
+def _gloo_worker(rank, world, port, tmpdir):
+    import torch.distributed as dist
+
+    from s3prl_b200 import parallel as P
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_items, T, D = 7, 5, 4
+        lens_all = [1000 + 37 * i for i in range(n_items)]
+        full = torch.arange(n_items * T * D, dtype=torch.float32).view(n_items, T, D)
+        lo, hi = P.shard_bounds(n_items, rank, world)
+        my_lens = P.shard_batch(lens_all, rank, world)
+        assert my_lens == lens_all[lo:hi]
+        assert P.global_max_len(my_lens) == max(lens_all)
+        out = P.gather_features(full[lo:hi].clone(), n_items)
+        assert torch.equal(out, full)
+        even = torch.arange(8 * T * D, dtype=torch.float32).view(8, T, D)
+        lo, hi = P.shard_bounds(8, rank, world)
+        assert torch.equal(P.gather_features(even[lo:hi].clone(), 8), even)
+        (Path(tmpdir) / f"ok{rank}").write_text("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_and_gather_gloo_world2(tmp_path):
+    import torch.multiprocessing as mp
+
+    from s3prl_b200 import parallel as P
+
+    # pure partition logic
+    for n in (1, 7, 32, 33):
+        for world in (1, 2, 3, 8):
+            spans = [P.shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
