@@ -118,6 +118,25 @@ class ClockSampler:
         }
 
 
+def usable_cores() -> int:
+    """Host cores this process may really use: min(affinity mask, cgroup v2/v1 CPU quota). On the GPU boxes
+    os.cpu_count() reports 128 while the container is capped at 16 CPUs; 128 threads would thrash."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = Path("/sys/fs/cgroup/cpu.max").read_text().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        try:
+            q = int(Path("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read_text())
+            p = int(Path("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read_text())
+            if q > 0:
+                n = min(n, max(1, q // p))
+        except Exception:
+            pass
+    return n
+
+
 def cpu_oracle_throughput(n_utts: int, steps: int, warmup: int):
     """Time the oracle port (torch-CPU restatement of the reference forward) on `n_utts` x 10 s of the workload."""
     import torch
@@ -127,7 +146,7 @@ def cpu_oracle_throughput(n_utts: int, steps: int, warmup: int):
     from s3prl_b200.upstream.configs import get_arch
     from s3prl_b200.upstream.weights import fabricate_state_dict
 
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     cfg = get_arch(MODEL)
     sd = fabricate_state_dict(cfg, seed=0)
@@ -152,7 +171,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     n_utts = 4 if cores < 48 else 8
     fps, ms, cores = cpu_oracle_throughput(n_utts, args.steps, args.warmup)
     sample = f"{n_utts} of the 32 utterances (x 10 s) per step; oracle port of the reference forward, torch-CPU fp32, {cores} threads"

@@ -31,13 +31,19 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
     lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
-// pack two floats -> two bf16x2 words (hi word, lo word); element 0 in the low half
+// pack two floats -> two bf16x2 words (hi word, lo word); element 0 in the low half.
+// 6 instructions per pair: cvt.rn.bf16x2, shl, lop, 2 x fsub, cvt.rn.bf16x2
 __device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    __nv_bfloat16 ah, al, bh, bl;
-    split_bf16(a, ah, al);
-    split_bf16(b, bh, bl);
-    hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
-    lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+    const float ra = a - __uint_as_float(hi << 16);
+    const float rb = b - __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+}
+
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -177,6 +183,18 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
 // Shared-memory matrix descriptor for a K-major bf16 tile stored as rows of 128 bytes with the
 // 128-byte swizzle (the layout TMA SWIZZLE_128B produces for a {64 x rows} bf16 box):
 //   8-row groups are 1024 B apart (SBO), LBO unused for swizzled K-major (set to 1), version 1 (sm_100).
+// Generic form: ROW_BYTES = 128 (SWIZZLE_128B, 8-row atoms 1024 B apart) or 64 (SWIZZLE_64B, atoms 512 B apart).
+template <int ROW_BYTES>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    static_assert(ROW_BYTES == 128 || ROW_BYTES == 64, "unsupported swizzle span");
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((8 * ROW_BYTES) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(ROW_BYTES == 128 ? 2 : 4) << 61;  // SWIZZLE_128B = 2, SWIZZLE_64B = 4
+    return d;
+}
 __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address, bits [0,14)

@@ -22,10 +22,11 @@ struct GemmParams {
     int tiles_m_per_batch;  // ceil(rows_per_batch / 128)
     int n_tiles;            // output column tiles
     int umma_n;             // columns per tile (multiple of 16, <= 256)
-    int num_k_blocks;       // k-blocks (of 64 elements) per output tile
-    // k-block kb reads   A box at (a_k_per_ntile*n_tile + (kb % kb_per_row)*64,
+    int block_k;            // bf16 elements per k-block: gemm_block_k(umma_n) (32 for 128x256 tiles, else 64)
+    int num_k_blocks;       // k-blocks per output tile
+    // k-block kb reads   A box at (a_k_per_ntile*n_tile + (kb % kb_per_row)*block_k,
     //                              row0 + (kb / kb_per_row)*a_row_step + a_row_off, batch)
-    //                    B box at (b_k_linear ? kb*64 : (kb % kb_per_row)*64, b_n_tiled ? n_tile*umma_n : 0,
+    //                    B box at (b_k_linear ? kb*block_k : (kb % kb_per_row)*block_k, b_n_tiled ? n_tile*umma_n : 0,
     //                              b_k_linear ? 0 : kb / kb_per_row + n_tile*b_z_per_ntile)
     int kb_per_row;
     int a_row_step;
@@ -55,6 +56,9 @@ struct GemmParams {
 
     double alg_flops;  // host-side accounting only: 2*M*N*K with the un-padded K
 };
+
+// k-block width the kernel instantiation for this tile width uses (tensor-map boxes must match)
+inline int gemm_block_k(int umma_n) { return umma_n > 128 ? 32 : 64; }
 
 // Launch on `stream`. Returns cudaGetLastError() of the launch.
 cudaError_t launch_gemm_bf16x3(const GemmParams& p, int sm_count, cudaStream_t stream);

@@ -21,16 +21,19 @@
 namespace s3b {
 
 static constexpr int kBlockM = 128;
-static constexpr int kBlockK = 64;               // bf16 elements = one 128-byte swizzle row
-static constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 static constexpr int kAccCols = 256;             // TMEM columns per accumulator stage
 static constexpr int kThreads = 256;
 
-template <int BLOCK_N>
+// BLOCK_K bf16 elements per pipeline stage = one swizzle row: 64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B.
+// 128x256 tiles use BLOCK_K = 32 so that four 48 KB stages fit (three loads in flight cover the TMA latency;
+// the first version had two 96 KB stages and ran the tensor pipe at ~60 %, profiles/r1a).
+template <int BLOCK_N, int BLOCK_K>
 struct GemmCfg {
-    static constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
+    static constexpr int kBlockK = BLOCK_K;
+    static constexpr int kATileBytes = kBlockM * BLOCK_K * 2;
+    static constexpr int kBTileBytes = BLOCK_N * BLOCK_K * 2;
     static constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;
-    static constexpr int kStages = (BLOCK_N >= 256) ? 2 : (BLOCK_N >= 128 ? 3 : 4);
+    static constexpr int kStages = (200 * 1024) / kStageBytes > 6 ? 6 : (200 * 1024) / kStageBytes;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -127,9 +130,11 @@ __device__ __forceinline__ void epilogue_cols(const GemmParams& p, const uint32_
     if (p.out_hi != nullptr) store_split<NC>(p.out_hi + off, p.out_lo + off, x);
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int BLOCK_K>
 __global__ void __launch_bounds__(kThreads, 1) gemm_bf16x3_kernel(const __grid_constant__ GemmParams p) {
-    using Cfg = GemmCfg<BLOCK_N>;
+    using Cfg = GemmCfg<BLOCK_N, BLOCK_K>;
+    constexpr int kBlockK = Cfg::kBlockK;
+    constexpr int kATileBytes = Cfg::kATileBytes;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment is required by the 128B swizzle atoms (8 rows x 128 B)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -220,10 +225,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16x3_kernel(const __grid_c
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + stage * Cfg::kStageBytes);
-                    const uint64_t da_hi = make_smem_desc_sw128(st);
-                    const uint64_t da_lo = make_smem_desc_sw128(st + kATileBytes);
-                    const uint64_t db_hi = make_smem_desc_sw128(st + 2 * kATileBytes);
-                    const uint64_t db_lo = make_smem_desc_sw128(st + 2 * kATileBytes + Cfg::kBTileBytes);
+                    const uint64_t da_hi = make_smem_desc<kBlockK * 2>(st);
+                    const uint64_t da_lo = make_smem_desc<kBlockK * 2>(st + kATileBytes);
+                    const uint64_t db_hi = make_smem_desc<kBlockK * 2>(st + 2 * kATileBytes);
+                    const uint64_t db_lo = make_smem_desc<kBlockK * 2>(st + 2 * kATileBytes + Cfg::kBTileBytes);
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
                         // advance 16 bf16 (= 32 bytes) along K inside the swizzle atom: +2 in (addr >> 4) units
@@ -287,12 +292,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16x3_kernel(const __grid_c
     }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int BLOCK_K>
 static cudaError_t launch_impl(const GemmParams& p, int sm_count, cudaStream_t stream) {
-    using Cfg = GemmCfg<BLOCK_N>;
+    using Cfg = GemmCfg<BLOCK_N, BLOCK_K>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf16x3_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16x3_kernel<BLOCK_N, BLOCK_K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::kSmemBytes);
         if (e != cudaSuccess) return e;
         attr_set = true;
@@ -300,15 +305,16 @@ static cudaError_t launch_impl(const GemmParams& p, int sm_count, cudaStream_t s
     const int num_tiles = p.batches * p.tiles_m_per_batch * p.n_tiles;
     if (num_tiles <= 0) return cudaSuccess;
     const int grid = num_tiles < sm_count ? num_tiles : sm_count;
-    gemm_bf16x3_kernel<BLOCK_N><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(p);
+    gemm_bf16x3_kernel<BLOCK_N, BLOCK_K><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_gemm_bf16x3(const GemmParams& p, int sm_count, cudaStream_t stream) {
     if (p.umma_n % 16 != 0 || p.umma_n < 16 || p.umma_n > 256) return cudaErrorInvalidValue;
-    if (p.umma_n > 128) return launch_impl<256>(p, sm_count, stream);
-    if (p.umma_n > 64) return launch_impl<128>(p, sm_count, stream);
-    return launch_impl<64>(p, sm_count, stream);
+    if (p.block_k != gemm_block_k(p.umma_n)) return cudaErrorInvalidValue;
+    if (p.umma_n > 128) return launch_impl<256, 32>(p, sm_count, stream);
+    if (p.umma_n > 64) return launch_impl<128, 64>(p, sm_count, stream);
+    return launch_impl<64, 64>(p, sm_count, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -341,8 +347,11 @@ int encode_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_
     cuuint64_t strides[2] = {stride1 * 2, stride2 * 2};  // bytes
     cuuint32_t box[3] = {box0, box1, 1};
     cuuint32_t estr[3] = {1, 1, 1};
+    // the swizzle span equals the box row: 64 elements -> 128 B, 32 elements -> 64 B
+    if (box0 != 64 && box0 != 32) return -2;
+    const CUtensorMapSwizzle sw = box0 == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return (int)r;
 }

@@ -482,14 +482,16 @@ static int pick_umma_n(int N) {
 static int linear_params(GemmParams& p, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo,
                          const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int64_t M, int N, int K) {
     memset(&p, 0, sizeof(p));
-    if (K % 64 != 0 || N % 16 != 0) return fail("linear: K %% 64 or N %% 16 violated (N=%d K=%d)", N, K);
+    if (K % 64 != 0 || N % 16 != 0)  // K % 64 keeps both k-block widths legal
+        return fail("linear: K %% 64 or N %% 16 violated (N=%d K=%d)", N, K);
     const int un = pick_umma_n(N);
-    TMAP_OK(encode_tmap_bf16_3d(&p.a_hi, a_hi, K, M, 1, K, (uint64_t)M * K, 64, 128));
-    TMAP_OK(encode_tmap_bf16_3d(&p.a_lo, a_lo, K, M, 1, K, (uint64_t)M * K, 64, 128));
-    TMAP_OK(encode_tmap_bf16_3d(&p.b_hi, w_hi, K, N, 1, K, (uint64_t)N * K, 64, un));
-    TMAP_OK(encode_tmap_bf16_3d(&p.b_lo, w_lo, K, N, 1, K, (uint64_t)N * K, 64, un));
+    const int bk = gemm_block_k(un);
+    TMAP_OK(encode_tmap_bf16_3d(&p.a_hi, a_hi, K, M, 1, K, (uint64_t)M * K, bk, 128));
+    TMAP_OK(encode_tmap_bf16_3d(&p.a_lo, a_lo, K, M, 1, K, (uint64_t)M * K, bk, 128));
+    TMAP_OK(encode_tmap_bf16_3d(&p.b_hi, w_hi, K, N, 1, K, (uint64_t)N * K, bk, un));
+    TMAP_OK(encode_tmap_bf16_3d(&p.b_lo, w_lo, K, N, 1, K, (uint64_t)N * K, bk, un));
     p.batches = 1, p.rows_per_batch = (int)M, p.tiles_m_per_batch = (int)((M + 127) / 128);
-    p.n_tiles = N / un, p.umma_n = un, p.num_k_blocks = K / 64, p.kb_per_row = K / 64;
+    p.n_tiles = N / un, p.umma_n = un, p.block_k = bk, p.num_k_blocks = K / bk, p.kb_per_row = K / bk;
     p.a_row_step = 0, p.a_row_off = 0, p.a_k_per_ntile = 0, p.b_n_tiled = 1, p.b_z_per_ntile = 0;
     p.out_rows_per_batch = (int)M;
     p.alg_flops = 2.0 * (double)M * N * K;
@@ -503,13 +505,14 @@ static int conv_params(GemmParams& p, const __nv_bfloat16* a_hi, const __nv_bflo
     memset(&p, 0, sizeof(p));
     const int C = kConvDim, K = kw * C;
     const uint64_t rows = (uint64_t)((Lin + 1) / 2);
-    TMAP_OK(encode_tmap_bf16_3d(&p.a_hi, a_hi, 2 * C, rows, B, 2 * C, (uint64_t)Lin * C, 64, 128));
-    TMAP_OK(encode_tmap_bf16_3d(&p.a_lo, a_lo, 2 * C, rows, B, 2 * C, (uint64_t)Lin * C, 64, 128));
+    const int bk = gemm_block_k(256);
+    TMAP_OK(encode_tmap_bf16_3d(&p.a_hi, a_hi, 2 * C, rows, B, 2 * C, (uint64_t)Lin * C, bk, 128));
+    TMAP_OK(encode_tmap_bf16_3d(&p.a_lo, a_lo, 2 * C, rows, B, 2 * C, (uint64_t)Lin * C, bk, 128));
     // weights [512][K], K index = tap*512 + channel, read linearly along K
-    TMAP_OK(encode_tmap_bf16_3d(&p.b_hi, w_hi, K, C, 1, K, (uint64_t)C * K, 64, 256));
-    TMAP_OK(encode_tmap_bf16_3d(&p.b_lo, w_lo, K, C, 1, K, (uint64_t)C * K, 64, 256));
+    TMAP_OK(encode_tmap_bf16_3d(&p.b_hi, w_hi, K, C, 1, K, (uint64_t)C * K, bk, 256));
+    TMAP_OK(encode_tmap_bf16_3d(&p.b_lo, w_lo, K, C, 1, K, (uint64_t)C * K, bk, 256));
     p.batches = B, p.rows_per_batch = (int)Lout, p.tiles_m_per_batch = (int)((Lout + 127) / 128);
-    p.n_tiles = C / 256, p.umma_n = 256, p.num_k_blocks = K / 64, p.kb_per_row = (2 * C) / 64;
+    p.n_tiles = C / 256, p.umma_n = 256, p.block_k = bk, p.num_k_blocks = K / bk, p.kb_per_row = (2 * C) / bk;
     p.a_row_step = 1, p.a_row_off = 0, p.a_k_per_ntile = 0, p.b_n_tiled = 1, p.b_z_per_ntile = 0, p.b_k_linear = 1;
     p.out_rows_per_batch = (int)Lout;
     p.alg_flops = 2.0 * (double)B * Lout * C * K;
@@ -526,7 +529,7 @@ static int posconv_params(GemmParams& p, const s3b_config& c, const __nv_bfloat1
     TMAP_OK(encode_tmap_bf16_3d(&p.b_hi, w_hi, 64, cpg, (uint64_t)G * Kp, 64, (uint64_t)cpg * 64, 64, cpg));
     TMAP_OK(encode_tmap_bf16_3d(&p.b_lo, w_lo, 64, cpg, (uint64_t)G * Kp, 64, (uint64_t)cpg * 64, 64, cpg));
     p.batches = B, p.rows_per_batch = T, p.tiles_m_per_batch = (T + 127) / 128;
-    p.n_tiles = G, p.umma_n = cpg, p.num_k_blocks = Kp, p.kb_per_row = 1;
+    p.n_tiles = G, p.umma_n = cpg, p.block_k = 64, p.num_k_blocks = Kp, p.kb_per_row = 1;
     p.a_row_step = 1, p.a_row_off = -(Kp / 2), p.a_k_per_ntile = cpg, p.b_n_tiled = 0, p.b_z_per_ntile = Kp;
     p.out_rows_per_batch = T;
     p.alg_flops = 2.0 * (double)B * T * D * cpg * Kp;
@@ -725,7 +728,8 @@ static int forward_impl(s3b_model* m, const float* const* wavs_dev, const int64_
             Epi e;
             e.bias = W.qkv_b.as<float>();
             set_epi(p, e, 3 * D);
-            p.qkv_mode = 1, p.T = T, p.Tp = Tp, p.H = H, p.D = D, p.q_scale = 0.125f;
+            // head_dim^-0.5 and log2(e): the attention kernel's softmax works in the exp2 domain
+            p.qkv_mode = 1, p.T = T, p.Tp = Tp, p.H = H, p.D = D, p.q_scale = 0.125f * 1.4426950408889634f;
             p.q_hi = m->q_s.h(), p.q_lo = m->q_s.l(), p.k_hi = m->k_s.h(), p.k_lo = m->k_s.l();
             p.vt_hi = m->vt_s.h(), p.vt_lo = m->vt_s.l();
         }
@@ -960,7 +964,7 @@ extern "C" int s3b_attention_f32(const float* q, const float* k, const float* v,
     S3B_OK(ctx.ensure(M * D));
     S3B_OK(kv.ensure(B * sizeof(int)));
     CUDA_OK(cudaMemcpyAsync(kv.p, valid_frames, B * sizeof(int), cudaMemcpyHostToDevice, st));
-    CUDA_OK(launch_qkv_scatter(q, k, v, B, T, Tp, H, 0.125f, qs.h(), qs.l(), ks.h(), ks.l(), vts.h(), vts.l(), st));
+    CUDA_OK(launch_qkv_scatter(q, k, v, B, T, Tp, H, 0.125f * 1.4426950408889634f, qs.h(), qs.l(), ks.h(), ks.l(), vts.h(), vts.l(), st));
     AttnParams ap;
     memset(&ap, 0, sizeof(ap));
     const uint64_t BH = (uint64_t)B * H;

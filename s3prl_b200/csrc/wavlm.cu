@@ -29,7 +29,8 @@ __global__ void rel_table_kernel(const float* __restrict__ emb, const int* __res
                                  float* __restrict__ table) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     const int h = blockIdx.y;
-    if (r < R) table[(size_t)h * R + r] = emb[(size_t)buckets[r] * H + h];
+    // pre-multiplied by log2(e): the attention kernel adds it to scores that live in the exp2 domain
+    if (r < R) table[(size_t)h * R + r] = emb[(size_t)buckets[r] * H + h] * 1.4426950408889634f;
 }
 
 cudaError_t launch_wavlm_rel_table(const float* emb, int num_buckets, int max_distance, int H, int T, float* table,
