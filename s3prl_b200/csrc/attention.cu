@@ -3,14 +3,16 @@
 // (s3prl/upstream/wav2vec2/wav2vec2_model.py:1146-1168) and, when bias_table is given, WavLM's gated
 // relative-position bias (s3prl/upstream/wavlm/modules.py:511-580).
 //
-// One CTA = one (batch, head, 128-query tile); thread i owns query row i (TMEM lane i). Two CTAs are co-resident
-// per SM (96 KB smem, 256 TMEM columns, 128 threads each) so that one CTA's softmax overlaps the other's MMAs.
-// Per 64-key block j:
+// One CTA = one (batch, head, 128-query tile), 160 threads:
+//   warps 0..3 : softmax warps, thread i owns query row i (TMEM lane i)
+//   warp 4     : control warp (lane 0): TMA loads and every tcgen05.mma / commit
+// Two CTAs are co-resident per SM (<= 204 registers/thread, ~97 KB smem, 256 TMEM columns each), so one CTA's
+// softmax overlaps the other's MMAs. Per 64-key block j:
 //   S_j  = Qhi*Khi^T + Qhi*Klo^T + Qlo*Khi^T    tcgen05.mma M=128 N=64 K=64 -> TMEM cols [64*(j&1), +64)
 //   online softmax in fp32 registers (scores arrive in the log2 domain: q was scaled by log2(e)/8),
-//   P split to bf16 hi/lo -> 128B-swizzled smem
+//   P split to bf16 hi/lo -> 128B-swizzled smem, mbarrier hand-off to the control warp (no __syncthreads)
 //   PV_j = Phi*Vhi + Phi*Vlo + Plo*Vhi          tcgen05.mma M=128 N=64 K=64 -> TMEM cols [128, 192)
-//   S_{j+1} is issued right behind PV_j (double-buffered S), O = O*alpha + PV_j in registers.
+//   S_{j+1} is queued right behind PV_j (double-buffered S); O = O*alpha + PV_j in registers.
 // K and V^T have one smem buffer each: K_{j+1} is re-loaded as soon as S_j has retired, V_{j+1} as soon as PV_j has.
 #include <math.h>
 
@@ -33,20 +35,23 @@ static constexpr int kOffP = kOffV + 2 * kKBytes;
 static constexpr int kOffBar = kOffP + 2 * kPBytes;
 static constexpr int kAttnSmem = kOffBar + 128 + 1024;  // 99,456 B -> two CTAs per SM
 static constexpr int kTmemCols = 256;                    // S0 | S1 | PV | (unused)
+static constexpr int kAttnThreads = 160;
 
 template <bool kBias>
-__global__ void __launch_bounds__(128, 2) attention_kernel(const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid_constant__ AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + kOffBar);
     uint64_t* bar_k = bar_q + 1;
     uint64_t* bar_v = bar_q + 2;
-    uint64_t* bar_s = bar_q + 3;  // [2]
-    uint64_t* bar_pv = bar_q + 5;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 6);
+    uint64_t* bar_s = bar_q + 3;   // [2]  S_j in TMEM (tcgen05.commit)
+    uint64_t* bar_pv = bar_q + 5;  //      PV_j in TMEM (tcgen05.commit)
+    uint64_t* bar_p = bar_q + 6;   //      P_j in smem and S_j consumed (one arrive per softmax warp)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 7);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
+    const int lane = tid & 31;
     const int q_tiles = (p.T + kQTile - 1) / kQTile;
     const int bh = blockIdx.x / q_tiles;
     const int q0 = (blockIdx.x - bh * q_tiles) * kQTile;
@@ -56,18 +61,22 @@ __global__ void __launch_bounds__(128, 2) attention_kernel(const __grid_constant
     const int nblk = (kv_len + kKBlk - 1) / kKBlk;
 
     if (tid == 0) {
-        tma_prefetch_desc(&p.q_hi);
-        tma_prefetch_desc(&p.k_hi);
-        tma_prefetch_desc(&p.vt_hi);
         mbar_init(bar_q, 1);
         mbar_init(bar_k, 1);
         mbar_init(bar_v, 1);
         mbar_init(&bar_s[0], 1);
         mbar_init(&bar_s[1], 1);
         mbar_init(bar_pv, 1);
+        mbar_init(bar_p, 4);
         fence_mbar_init();
     }
-    if (warp == 0) {
+    if (warp == 4) {
+        if (lane == 0) {
+            tma_prefetch_desc(&p.q_hi);
+            tma_prefetch_desc(&p.k_hi);
+            tma_prefetch_desc(&p.vt_hi);
+        }
+        __syncwarp();
         tmem_alloc(tmem_slot, kTmemCols);
         tmem_relinquish();
     }
@@ -76,182 +85,183 @@ __global__ void __launch_bounds__(128, 2) attention_kernel(const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_o = tmem_base + 128;
-    const uint32_t lane_off = ((uint32_t)(warp * 32)) << 16;
-    const uint32_t idesc = make_idesc_bf16(kQTile, 64);
 
-    auto load_k = [&](int j) {
-        mbar_arrive_expect_tx(bar_k, 2 * kKBytes);
-        tma_load_3d(smem + kOffK, &p.k_hi, bar_k, 0, j * kKBlk, bh);
-        tma_load_3d(smem + kOffK + kKBytes, &p.k_lo, bar_k, 0, j * kKBlk, bh);
-    };
-    auto load_v = [&](int j) {
-        mbar_arrive_expect_tx(bar_v, 2 * kKBytes);
-        tma_load_3d(smem + kOffV, &p.vt_hi, bar_v, j * kKBlk, 0, bh);
-        tma_load_3d(smem + kOffV + kKBytes, &p.vt_lo, bar_v, j * kKBlk, 0, bh);
-    };
-    auto issue_s = [&](int j) {  // S_j = Q K_j^T into S buffer j&1
-        const uint32_t qa = smem_u32(smem + kOffQ), ka = smem_u32(smem + kOffK);
-        const uint64_t dq_hi = make_smem_desc_sw128(qa), dq_lo = make_smem_desc_sw128(qa + kQBytes);
-        const uint64_t dk_hi = make_smem_desc_sw128(ka), dk_lo = make_smem_desc_sw128(ka + kKBytes);
-        const uint32_t d = tmem_base + (uint32_t)(j & 1) * 64u;
-#pragma unroll
-        for (int k = 0; k < kHd / 16; ++k) {
-            const uint64_t ko = (uint64_t)(2 * k);
-            umma_bf16(d, dq_lo + ko, dk_hi + ko, idesc, k != 0 ? 1u : 0u);
-            umma_bf16(d, dq_hi + ko, dk_lo + ko, idesc, 1u);
-            umma_bf16(d, dq_hi + ko, dk_hi + ko, idesc, 1u);
-        }
-        umma_commit(&bar_s[j & 1]);
-    };
-
-    if (tid == 0) {
-        mbar_arrive_expect_tx(bar_q, 2 * kQBytes);
-        tma_load_3d(smem + kOffQ, &p.q_hi, bar_q, 0, q0, bh);
-        tma_load_3d(smem + kOffQ + kQBytes, &p.q_lo, bar_q, 0, q0, bh);
-        load_k(0);
-        load_v(0);
-        mbar_wait(bar_q, 0);
-        mbar_wait(bar_k, 0);
-        tc_fence_after();
-        issue_s(0);
-    }
-
-    const int q_row = q0 + tid;
-    const bool row_ok = q_row < p.T;
-    float gate = 0.f;
-    const float* brow = nullptr;
-    if (kBias) {
-        gate = (p.gate == nullptr) ? 1.0f : (row_ok ? p.gate[((size_t)b * p.H + h) * p.T + q_row] : 0.f);
-        brow = p.bias_table + (size_t)h * (2 * p.T - 1) + (p.T - 1 - (row_ok ? q_row : 0));  // index by key k
-    }
-
-    float o[kHd];
-#pragma unroll
-    for (int d = 0; d < kHd; ++d) o[d] = 0.f;
-    float m_run = -INFINITY;  // running row max (log2 domain)
-    float l_run = 0.f;
-
-    uint8_t* p_hi_s = smem + kOffP;
-    uint8_t* p_lo_s = smem + kOffP + kPBytes;
-    // 128B-swizzle placement of this thread's row inside a [128 x 64] bf16 K-major tile
-    const uint32_t row_off = (uint32_t)(tid >> 3) * 1024u + (uint32_t)(tid & 7) * 128u;
-    const uint32_t row_xor = (uint32_t)(tid & 7);
-
-    for (int j = 0; j < nblk; ++j) {
-        mbar_wait(&bar_s[j & 1], (uint32_t)((j >> 1) & 1));
-        __syncwarp();
-        tc_fence_after();
-        if (tid == 0 && j + 1 < nblk) load_k(j + 1);  // S_j retired: the K buffer is free
-
-        // ---- scores of this thread's row -> registers -------------------------------------------------
-        float s[kKBlk];
-        {
-            const uint32_t ts = tmem_base + (uint32_t)(j & 1) * 64u + lane_off;
-            uint32_t v0[32], v1[32];
-            tmem_ld_32x32(ts, v0);
-            tmem_ld_32x32(ts + 32, v1);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(v0[i]), s[32 + i] = __uint_as_float(v1[i]);
-        }
-        const int kbase = j * kKBlk;
-        if (kBias) {
-#pragma unroll
-            for (int i = 0; i < kKBlk; ++i) {
-                const int kk = kbase + i;
-                s[i] = fmaf(gate, (kk < p.T) ? __ldg(brow + kk) : 0.f, s[i]);
-            }
-        }
-        if (kbase + kKBlk > kv_len) {  // block-uniform: only the last block is partially masked
-#pragma unroll
-            for (int i = 0; i < kKBlk; ++i)
-                if (kbase + i >= kv_len) s[i] = -INFINITY;
-        }
-        float mx = s[0];
-#pragma unroll
-        for (int i = 1; i < kKBlk; ++i) mx = fmaxf(mx, s[i]);
-        const float m_new = fmaxf(m_run, mx);  // finite: key kbase is always valid
-        const float alpha = fast_exp2(m_run - m_new);
-        float psum0 = 0.f, psum1 = 0.f;
-#pragma unroll
-        for (int i = 0; i < kKBlk; i += 8) {
-            uint32_t hw[4], lw[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float p0 = fast_exp2(s[i + 2 * e] - m_new);
-                const float p1 = fast_exp2(s[i + 2 * e + 1] - m_new);
-                psum0 += p0, psum1 += p1;
-                split_pack2(p0, p1, hw[e], lw[e]);
-            }
-            const uint32_t chunk = ((uint32_t)(i >> 3) ^ row_xor) * 16u;
-            *reinterpret_cast<uint4*>(p_hi_s + row_off + chunk) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *reinterpret_cast<uint4*>(p_lo_s + row_off + chunk) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-        }
-        l_run = fmaf(l_run, alpha, psum0 + psum1);
-        m_run = m_new;
-
-        fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor-core async proxy
-        tc_fence_before();         // orders this thread's tcgen05.ld of S_j before the barrier
-        __syncthreads();
-
-        if (tid == 0) {
-            tc_fence_after();
-            mbar_wait(bar_v, (uint32_t)(j & 1));
-            tc_fence_after();
-            const uint32_t pa = smem_u32(p_hi_s), va = smem_u32(smem + kOffV);
-            const uint64_t dp_hi = make_smem_desc_sw128(pa), dp_lo = make_smem_desc_sw128(pa + kPBytes);
+    if (warp == 4) {
+        // ===================== control warp: TMA + MMA issue =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(kQTile, 64);
+            const uint32_t qa = smem_u32(smem + kOffQ), ka = smem_u32(smem + kOffK);
+            const uint32_t va = smem_u32(smem + kOffV), pa = smem_u32(smem + kOffP);
+            const uint64_t dq_hi = make_smem_desc_sw128(qa), dq_lo = make_smem_desc_sw128(qa + kQBytes);
+            const uint64_t dk_hi = make_smem_desc_sw128(ka), dk_lo = make_smem_desc_sw128(ka + kKBytes);
             const uint64_t dv_hi = make_smem_desc_sw128(va), dv_lo = make_smem_desc_sw128(va + kKBytes);
+            const uint64_t dp_hi = make_smem_desc_sw128(pa), dp_lo = make_smem_desc_sw128(pa + kPBytes);
+            auto load_k = [&](int j) {
+                mbar_arrive_expect_tx(bar_k, 2 * kKBytes);
+                tma_load_3d(smem + kOffK, &p.k_hi, bar_k, 0, j * kKBlk, bh);
+                tma_load_3d(smem + kOffK + kKBytes, &p.k_lo, bar_k, 0, j * kKBlk, bh);
+            };
+            auto load_v = [&](int j) {
+                mbar_arrive_expect_tx(bar_v, 2 * kKBytes);
+                tma_load_3d(smem + kOffV, &p.vt_hi, bar_v, j * kKBlk, 0, bh);
+                tma_load_3d(smem + kOffV + kKBytes, &p.vt_lo, bar_v, j * kKBlk, 0, bh);
+            };
+            auto issue_s = [&](int j) {  // S_j = Q K_j^T into S buffer j&1
+                const uint32_t d = tmem_base + (uint32_t)(j & 1) * 64u;
 #pragma unroll
-            for (int k = 0; k < kKBlk / 16; ++k) {
-                const uint64_t ko = (uint64_t)(2 * k);
-                umma_bf16(tmem_o, dp_lo + ko, dv_hi + ko, idesc, k != 0 ? 1u : 0u);
-                umma_bf16(tmem_o, dp_hi + ko, dv_lo + ko, idesc, 1u);
-                umma_bf16(tmem_o, dp_hi + ko, dv_hi + ko, idesc, 1u);
-            }
-            umma_commit(bar_pv);
-            if (j + 1 < nblk) {  // queue S_{j+1} right behind PV_j (its S buffer was last read in iteration j-1)
-                mbar_wait(bar_k, (uint32_t)((j + 1) & 1));
+                for (int k = 0; k < kHd / 16; ++k) {
+                    const uint64_t ko = (uint64_t)(2 * k);
+                    umma_bf16(d, dq_lo + ko, dk_hi + ko, idesc, k != 0 ? 1u : 0u);
+                    umma_bf16(d, dq_hi + ko, dk_lo + ko, idesc, 1u);
+                    umma_bf16(d, dq_hi + ko, dk_hi + ko, idesc, 1u);
+                }
+                umma_commit(&bar_s[j & 1]);
+            };
+            mbar_arrive_expect_tx(bar_q, 2 * kQBytes);
+            tma_load_3d(smem + kOffQ, &p.q_hi, bar_q, 0, q0, bh);
+            tma_load_3d(smem + kOffQ + kQBytes, &p.q_lo, bar_q, 0, q0, bh);
+            load_k(0);
+            load_v(0);
+            mbar_wait(bar_q, 0);
+            mbar_wait(bar_k, 0);
+            tc_fence_after();
+            issue_s(0);
+            for (int j = 0; j < nblk; ++j) {
+                const bool more = j + 1 < nblk;
+                mbar_wait(&bar_s[j & 1], (uint32_t)((j >> 1) & 1));  // S_j retired: the K buffer is free
+                if (more) load_k(j + 1);
+                mbar_wait(bar_p, (uint32_t)(j & 1));                  // P_j in smem, S_j consumed by every row
+                mbar_wait(bar_v, (uint32_t)(j & 1));
                 tc_fence_after();
-                issue_s(j + 1);
-            }
-        }
-        mbar_wait(bar_pv, (uint32_t)(j & 1));
-        __syncwarp();
-        tc_fence_after();
-        if (tid == 0 && j + 1 < nblk) load_v(j + 1);  // PV_j retired: the V buffer (and the P tile) are free
-        {
-            uint32_t v0[32], v1[32];
-            tmem_ld_32x32(tmem_o + lane_off, v0);
-            tmem_ld_32x32(tmem_o + lane_off + 32, v1);
-            tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                o[i] = fmaf(o[i], alpha, __uint_as_float(v0[i]));
-                o[32 + i] = fmaf(o[32 + i], alpha, __uint_as_float(v1[i]));
+                for (int k = 0; k < kKBlk / 16; ++k) {
+                    const uint64_t ko = (uint64_t)(2 * k);
+                    umma_bf16(tmem_o, dp_lo + ko, dv_hi + ko, idesc, k != 0 ? 1u : 0u);
+                    umma_bf16(tmem_o, dp_hi + ko, dv_lo + ko, idesc, 1u);
+                    umma_bf16(tmem_o, dp_hi + ko, dv_hi + ko, idesc, 1u);
+                }
+                umma_commit(bar_pv);
+                if (more) {  // queue S_{j+1} right behind PV_j (its S buffer was consumed in iteration j-1)
+                    mbar_wait(bar_k, (uint32_t)((j + 1) & 1));
+                    tc_fence_after();
+                    issue_s(j + 1);
+                }
+                mbar_wait(bar_pv, (uint32_t)(j & 1));  // PV_j retired: the V buffer is free
+                if (more) load_v(j + 1);
             }
         }
-        // No barrier here: PV_{j+1} (the next writer of the PV columns) and the next P tile stores are both
-        // ordered behind the next iteration's __syncthreads / bar_pv wait.
-    }
+    } else {
+        // ===================== softmax warps =====================
+        const uint32_t lane_off = ((uint32_t)(warp * 32)) << 16;
+        const int q_row = q0 + tid;
+        const bool row_ok = q_row < p.T;
+        float gate = 0.f;
+        const float* brow = nullptr;
+        if (kBias) {
+            gate = (p.gate == nullptr) ? 1.0f : (row_ok ? p.gate[((size_t)b * p.H + h) * p.T + q_row] : 0.f);
+            brow = p.bias_table + (size_t)h * (2 * p.T - 1) + (p.T - 1 - (row_ok ? q_row : 0));  // index by key k
+        }
+        float o[kHd];
+#pragma unroll
+        for (int d = 0; d < kHd; ++d) o[d] = 0.f;
+        float m_run = -INFINITY;  // running row max (log2 domain)
+        float l_run = 0.f;
+        uint8_t* p_hi_s = smem + kOffP;
+        uint8_t* p_lo_s = smem + kOffP + kPBytes;
+        // 128B-swizzle placement of this thread's row inside a [128 x 64] bf16 K-major tile
+        const uint32_t row_off = (uint32_t)(tid >> 3) * 1024u + (uint32_t)(tid & 7) * 128u;
+        const uint32_t row_xor = (uint32_t)(tid & 7);
 
-    if (row_ok) {
-        const float inv = 1.0f / l_run;
-        const size_t off = ((size_t)b * p.T + q_row) * (size_t)p.D + (size_t)h * kHd;
-        uint4* dh = reinterpret_cast<uint4*>(p.ctx_hi + off);
-        uint4* dl = reinterpret_cast<uint4*>(p.ctx_lo + off);
+        for (int j = 0; j < nblk; ++j) {
+            mbar_wait(&bar_s[j & 1], (uint32_t)((j >> 1) & 1));
+            __syncwarp();
+            tc_fence_after();
+            float s[kKBlk];
+            {
+                const uint32_t ts = tmem_base + (uint32_t)(j & 1) * 64u + lane_off;
+                uint32_t v0[32], v1[32];
+                tmem_ld_32x32(ts, v0);
+                tmem_ld_32x32(ts + 32, v1);
+                tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < kHd; i += 8) {
-            uint32_t hw[4], lw[4];
+                for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(v0[i]), s[32 + i] = __uint_as_float(v1[i]);
+            }
+            const int kbase = j * kKBlk;
+            if (kBias) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) split_pack2(o[i + 2 * e] * inv, o[i + 2 * e + 1] * inv, hw[e], lw[e]);
-            dh[i >> 3] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            dl[i >> 3] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                for (int i = 0; i < kKBlk; ++i) {
+                    const int kk = kbase + i;
+                    s[i] = fmaf(gate, (kk < p.T) ? __ldg(brow + kk) : 0.f, s[i]);
+                }
+            }
+            if (kbase + kKBlk > kv_len) {  // block-uniform: only the last block is partially masked
+#pragma unroll
+                for (int i = 0; i < kKBlk; ++i)
+                    if (kbase + i >= kv_len) s[i] = -INFINITY;
+            }
+            float mx = s[0];
+#pragma unroll
+            for (int i = 1; i < kKBlk; ++i) mx = fmaxf(mx, s[i]);
+            const float m_new = fmaxf(m_run, mx);  // finite: key kbase is always valid
+            const float alpha = fast_exp2(m_run - m_new);
+            float psum0 = 0.f, psum1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < kKBlk; i += 8) {
+                uint32_t hw[4], lw[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float p0 = fast_exp2(s[i + 2 * e] - m_new);
+                    const float p1 = fast_exp2(s[i + 2 * e + 1] - m_new);
+                    psum0 += p0, psum1 += p1;
+                    split_pack2(p0, p1, hw[e], lw[e]);
+                }
+                const uint32_t chunk = ((uint32_t)(i >> 3) ^ row_xor) * 16u;
+                *reinterpret_cast<uint4*>(p_hi_s + row_off + chunk) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                *reinterpret_cast<uint4*>(p_lo_s + row_off + chunk) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+            l_run = fmaf(l_run, alpha, psum0 + psum1);
+            m_run = m_new;
+
+            fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor-core async proxy
+            tc_fence_before();         // orders this thread's tcgen05.ld of S_j / PV_{j-1} before the hand-off
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_p);
+
+            mbar_wait(bar_pv, (uint32_t)(j & 1));
+            __syncwarp();
+            tc_fence_after();
+            {
+                uint32_t v0[32], v1[32];
+                tmem_ld_32x32(tmem_o + lane_off, v0);
+                tmem_ld_32x32(tmem_o + lane_off + 32, v1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    o[i] = fmaf(o[i], alpha, __uint_as_float(v0[i]));
+                    o[32 + i] = fmaf(o[32 + i], alpha, __uint_as_float(v1[i]));
+                }
+            }
+        }
+
+        if (row_ok) {
+            const float inv = 1.0f / l_run;
+            const size_t off = ((size_t)b * p.T + q_row) * (size_t)p.D + (size_t)h * kHd;
+            uint4* dh = reinterpret_cast<uint4*>(p.ctx_hi + off);
+            uint4* dl = reinterpret_cast<uint4*>(p.ctx_lo + off);
+#pragma unroll
+            for (int i = 0; i < kHd; i += 8) {
+                uint32_t hw[4], lw[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split_pack2(o[i + 2 * e] * inv, o[i + 2 * e + 1] * inv, hw[e], lw[e]);
+                dh[i >> 3] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                dl[i >> 3] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) {
+    if (warp == 4) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }
@@ -270,8 +280,8 @@ cudaError_t launch_attention(const AttnParams& p, cudaStream_t s) {
     const int q_tiles = (p.T + kQTile - 1) / kQTile;
     const int grid = p.B * p.H * q_tiles;
     if (grid <= 0) return cudaSuccess;
-    if (p.bias_table != nullptr) attention_kernel<true><<<grid, 128, kAttnSmem, s>>>(p);
-    else attention_kernel<false><<<grid, 128, kAttnSmem, s>>>(p);
+    if (p.bias_table != nullptr) attention_kernel<true><<<grid, kAttnThreads, kAttnSmem, s>>>(p);
+    else attention_kernel<false><<<grid, kAttnThreads, kAttnSmem, s>>>(p);
     return cudaGetLastError();
 }
 
