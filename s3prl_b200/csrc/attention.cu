@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
 
     if (warp == 4) {
         // ===================== control warp: TMA + MMA issue =====================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = make_idesc_bf16(kQTile, 64);
             const uint32_t qa = smem_u32(smem + kOffQ), ka = smem_u32(smem + kOffK);
             const uint32_t va = smem_u32(smem + kOffV), pa = smem_u32(smem + kOffP);

@@ -46,6 +46,21 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
+// One lane of a CONVERGED warp. Unlike `lane == 0`, ptxas knows that the region guarded by elect.sync is
+// single-threaded and feeds tcgen05 / TMA operands through uniform registers directly (no per-instruction
+// ELECT/R2UR waterfall loop: ~50 issue cycles saved per tcgen05.mma).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
