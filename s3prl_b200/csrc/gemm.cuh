@@ -22,6 +22,7 @@ struct GemmParams {
     int tiles_m_per_batch;  // ceil(rows_per_batch / 128)
     int n_tiles;            // output column tiles
     int umma_n;             // columns per tile (multiple of 16, <= 256)
+    int two_cta;            // 1: CTA-pair kernel (umma_n == 256, block_k == 64, B boxes hold umma_n/2 rows)
     int block_k;            // bf16 elements per k-block: gemm_block_k(umma_n) (32 for 128x256 tiles, else 64)
     int num_k_blocks;       // k-blocks per output tile
     // k-block kb reads   A box at (a_k_per_ntile*n_tile + (kb % kb_per_row)*block_k,

@@ -292,6 +292,198 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16x3_kernel(const __grid_c
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2) for 256-column tiles: one 256 x 256 output tile per cluster of two CTAs.
+// Each CTA loads its own 128 rows of A (hi, lo) and 128 of the 256 W rows (hi, lo): 64 KB per 64-wide k-block
+// instead of 96 KB, and every tcgen05.mma reads 8 KB instead of 12 KB of local shared memory — the single-CTA
+// kernel is bound by shared-memory bandwidth (TMA writes + operand reads ~158 B/clk vs 128 B/clk available).
+// Protocol: TMA of both CTAs credits the LEADER's full barrier; the leader issues M=256 MMAs and multicasts its
+// commits to both CTAs' empty / tmem_full barriers; both epilogues (128 rows each) arrive on the leader's
+// tmem_empty barrier.
+// ------------------------------------------------------------------------------------------------
+static constexpr int k2BlockK = 64;
+static constexpr int k2TileBytes = 128 * k2BlockK * 2;    // 16 KB: A plane (128 rows) or half-B plane (128 rows)
+static constexpr int k2StageBytes = 4 * k2TileBytes;      // A_hi A_lo B_hi B_lo
+static constexpr int k2Stages = 3;
+static constexpr int k2SmemBytes = k2Stages * k2StageBytes + 1024 + 256;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    gemm2_bf16x3_kernel(const __grid_constant__ GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + k2Stages * k2StageBytes);
+    uint64_t* full_bar = bars;                   // [k2Stages] used in the leader only (count 2 + tx bytes)
+    uint64_t* empty_bar = bars + k2Stages;       // [k2Stages] one per CTA, multicast commit
+    uint64_t* tmem_full = bars + 2 * k2Stages;   // [2]        one per CTA, multicast commit
+    uint64_t* tmem_empty = tmem_full + 2;        // [2]        leader only (8 epilogue warps)
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    cluster_sync_all();  // both CTAs resident before the paired TMEM allocation
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&p.a_hi);
+        tma_prefetch_desc(&p.a_lo);
+        tma_prefetch_desc(&p.b_hi);
+        tma_prefetch_desc(&p.b_lo);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int s = 0; s < k2Stages; ++s) {
+            mbar_init(&full_bar[s], 2);  // leader's expect_tx arrive + the peer's remote arrive
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tmem_full[s], 1);
+            mbar_init(&tmem_empty[s], 8);  // 4 epilogue warps x 2 CTAs
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc_2cta(tmem_base_slot, 2 * kAccCols);
+        tmem_relinquish_2cta();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    const int pairs_per_batch = (p.tiles_m_per_batch + 1) >> 1;
+    const int num_pt = p.batches * pairs_per_batch * p.n_tiles;
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int pt = cluster_id; pt < num_pt; pt += num_clusters) {
+                const int n_tile = pt % p.n_tiles;
+                const int mp = pt / p.n_tiles;
+                const int batch = mp / pairs_per_batch;
+                const int row0 = ((mp - batch * pairs_per_batch) * 2 + (int)rank) * kBlockM;
+                const int a_k0 = p.a_k_per_ntile * n_tile;
+                const int b_n0 = n_tile * p.umma_n + (int)rank * (p.umma_n >> 1);
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    const int kq = kb / p.kb_per_row;
+                    const int kr = kb - kq * p.kb_per_row;
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    uint8_t* st = smem + stage * k2StageBytes;
+                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * k2StageBytes);
+                    else mbar_arrive_remote(&full_bar[stage], 0);
+                    const int a_row = row0 + kq * p.a_row_step + p.a_row_off;
+                    tma_load_3d_2cta(st, &p.a_hi, &full_bar[stage], a_k0 + kr * k2BlockK, a_row, batch);
+                    tma_load_3d_2cta(st + k2TileBytes, &p.a_lo, &full_bar[stage], a_k0 + kr * k2BlockK, a_row, batch);
+                    const int b_k = (p.b_k_linear ? kb : kr) * k2BlockK;
+                    tma_load_3d_2cta(st + 2 * k2TileBytes, &p.b_hi, &full_bar[stage], b_k, b_n0, 0);
+                    tma_load_3d_2cta(st + 3 * k2TileBytes, &p.b_lo, &full_bar[stage], b_k, b_n0, 0);
+                    if (++stage == k2Stages) stage = 0, phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1 && leader) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_bf16(2 * kBlockM, (uint32_t)p.umma_n);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            int done = 0;
+            for (int pt = cluster_id; pt < num_pt; pt += num_clusters, ++done) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccCols;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + stage * k2StageBytes);
+                    const uint64_t da_hi = make_smem_desc<128>(st);
+                    const uint64_t da_lo = make_smem_desc<128>(st + k2TileBytes);
+                    const uint64_t db_hi = make_smem_desc<128>(st + 2 * k2TileBytes);
+                    const uint64_t db_lo = make_smem_desc<128>(st + 3 * k2TileBytes);
+#pragma unroll
+                    for (int k = 0; k < k2BlockK / 16; ++k) {
+                        const uint64_t ko = (uint64_t)(k * 2);
+                        umma_bf16_2cta(d_tmem, da_lo + ko, db_hi + ko, idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_bf16_2cta(d_tmem, da_hi + ko, db_lo + ko, idesc, 1u);
+                        umma_bf16_2cta(d_tmem, da_hi + ko, db_hi + ko, idesc, 1u);
+                    }
+                    umma_commit_2cta(&empty_bar[stage]);
+                    if (++stage == k2Stages) stage = 0, phase ^= 1u;
+                }
+                umma_commit_2cta(&tmem_full[acc]);
+                if (++acc == 2) acc = 0, acc_phase ^= 1u;
+            }
+            // the peer's epilogue arrives remotely on this CTA's tmem_empty barriers: drain before teardown
+            if (done > 0) {
+                const int last = done - 1;
+                mbar_wait(&tmem_empty[last & 1], (uint32_t)((last >> 1) & 1));
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (both CTAs, 128 rows each) =====================
+        const int ew = warp - 4;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int pt = cluster_id; pt < num_pt; pt += num_clusters) {
+            const int n_tile = pt % p.n_tiles;
+            const int mp = pt / p.n_tiles;
+            const int batch = mp / pairs_per_batch;
+            const int row0 = ((mp - batch * pairs_per_batch) * 2 + (int)rank) * kBlockM;
+            const int row = row0 + ew * 32 + lane;
+            const bool row_ok = row < p.rows_per_batch;
+            const size_t m = (size_t)batch * p.out_rows_per_batch + (row_ok ? row : 0);
+            const bool masked = (p.row_mask != nullptr) && row_ok && (p.row_mask[m] != 0);
+            const int col0 = n_tile * p.umma_n;
+
+            mbar_wait(&tmem_full[acc], acc_phase);
+            __syncwarp();
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * kAccCols;
+            for (int c = 0; c + 32 <= p.umma_n; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_row + (uint32_t)c, v);
+                tmem_ld_wait();
+                epilogue_cols<32>(p, v, row_ok, m, col0 + c, masked);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (leader) mbar_arrive(&tmem_empty[acc]);
+                else mbar_arrive_remote(&tmem_empty[acc], 0);
+            }
+            if (++acc == 2) acc = 0, acc_phase ^= 1u;
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2cta(tmem_base, 2 * kAccCols);
+    }
+}
+
+static cudaError_t launch_pair(const GemmParams& p, int sm_count, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e =
+            cudaFuncSetAttribute(gemm2_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    if (p.umma_n != 256 || p.block_k != k2BlockK || !p.b_n_tiled || p.b_z_per_ntile != 0) return cudaErrorInvalidValue;
+    const int num_pt = p.batches * ((p.tiles_m_per_batch + 1) / 2) * p.n_tiles;
+    if (num_pt <= 0) return cudaSuccess;
+    const int clusters = num_pt < sm_count / 2 ? num_pt : sm_count / 2;
+    gemm2_bf16x3_kernel<<<2 * clusters, kThreads, k2SmemBytes, stream>>>(p);
+    return cudaGetLastError();
+}
+
 template <int BLOCK_N, int BLOCK_K>
 static cudaError_t launch_impl(const GemmParams& p, int sm_count, cudaStream_t stream) {
     using Cfg = GemmCfg<BLOCK_N, BLOCK_K>;
@@ -311,6 +503,7 @@ static cudaError_t launch_impl(const GemmParams& p, int sm_count, cudaStream_t s
 
 cudaError_t launch_gemm_bf16x3(const GemmParams& p, int sm_count, cudaStream_t stream) {
     if (p.umma_n % 16 != 0 || p.umma_n < 16 || p.umma_n > 256) return cudaErrorInvalidValue;
+    if (p.two_cta) return launch_pair(p, sm_count, stream);
     if (p.block_k != gemm_block_k(p.umma_n)) return cudaErrorInvalidValue;
     if (p.umma_n > 128) return launch_impl<256, 32>(p, sm_count, stream);
     if (p.umma_n > 64) return launch_impl<128, 64>(p, sm_count, stream);

@@ -13,6 +13,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -463,6 +464,16 @@ static void set_epi(GemmParams& p, const Epi& e, int ldo) {
     p.qkv_mode = 0;
 }
 
+// 256-column tiles run on CTA pairs (cta_group::2) unless S3B_GEMM_PAIR=0 (kept for A/B measurements)
+static int use_cta_pairs(int umma_n) {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("S3B_GEMM_PAIR");
+        enabled = (e == nullptr || e[0] != '0') ? 1 : 0;
+    }
+    return (umma_n == 256 && enabled) ? 1 : 0;
+}
+
 static int pick_umma_n(int N) {
     if (N % 256 == 0) return 256;
     if (N % 192 == 0) return 192;
@@ -485,11 +496,14 @@ static int linear_params(GemmParams& p, const __nv_bfloat16* a_hi, const __nv_bf
     if (K % 64 != 0 || N % 16 != 0)  // K % 64 keeps both k-block widths legal
         return fail("linear: K %% 64 or N %% 16 violated (N=%d K=%d)", N, K);
     const int un = pick_umma_n(N);
-    const int bk = gemm_block_k(un);
+    const int pair = use_cta_pairs(un);
+    const int bk = pair ? 64 : gemm_block_k(un);
+    const int bbox = pair ? un / 2 : un;  // CTA pairs: each CTA loads half of the tile's W rows
     TMAP_OK(encode_tmap_bf16_3d(&p.a_hi, a_hi, K, M, 1, K, (uint64_t)M * K, bk, 128));
     TMAP_OK(encode_tmap_bf16_3d(&p.a_lo, a_lo, K, M, 1, K, (uint64_t)M * K, bk, 128));
-    TMAP_OK(encode_tmap_bf16_3d(&p.b_hi, w_hi, K, N, 1, K, (uint64_t)N * K, bk, un));
-    TMAP_OK(encode_tmap_bf16_3d(&p.b_lo, w_lo, K, N, 1, K, (uint64_t)N * K, bk, un));
+    TMAP_OK(encode_tmap_bf16_3d(&p.b_hi, w_hi, K, N, 1, K, (uint64_t)N * K, bk, bbox));
+    TMAP_OK(encode_tmap_bf16_3d(&p.b_lo, w_lo, K, N, 1, K, (uint64_t)N * K, bk, bbox));
+    p.two_cta = pair;
     p.batches = 1, p.rows_per_batch = (int)M, p.tiles_m_per_batch = (int)((M + 127) / 128);
     p.n_tiles = N / un, p.umma_n = un, p.block_k = bk, p.num_k_blocks = K / bk, p.kb_per_row = K / bk;
     p.a_row_step = 0, p.a_row_off = 0, p.a_k_per_ntile = 0, p.b_n_tiled = 1, p.b_z_per_ntile = 0;
@@ -505,12 +519,15 @@ static int conv_params(GemmParams& p, const __nv_bfloat16* a_hi, const __nv_bflo
     memset(&p, 0, sizeof(p));
     const int C = kConvDim, K = kw * C;
     const uint64_t rows = (uint64_t)((Lin + 1) / 2);
-    const int bk = gemm_block_k(256);
+    const int pair = use_cta_pairs(256);
+    const int bk = pair ? 64 : gemm_block_k(256);
+    const int bbox = pair ? 128 : 256;
     TMAP_OK(encode_tmap_bf16_3d(&p.a_hi, a_hi, 2 * C, rows, B, 2 * C, (uint64_t)Lin * C, bk, 128));
     TMAP_OK(encode_tmap_bf16_3d(&p.a_lo, a_lo, 2 * C, rows, B, 2 * C, (uint64_t)Lin * C, bk, 128));
     // weights [512][K], K index = tap*512 + channel, read linearly along K
-    TMAP_OK(encode_tmap_bf16_3d(&p.b_hi, w_hi, K, C, 1, K, (uint64_t)C * K, bk, 256));
-    TMAP_OK(encode_tmap_bf16_3d(&p.b_lo, w_lo, K, C, 1, K, (uint64_t)C * K, bk, 256));
+    TMAP_OK(encode_tmap_bf16_3d(&p.b_hi, w_hi, K, C, 1, K, (uint64_t)C * K, bk, bbox));
+    TMAP_OK(encode_tmap_bf16_3d(&p.b_lo, w_lo, K, C, 1, K, (uint64_t)C * K, bk, bbox));
+    p.two_cta = pair;
     p.batches = B, p.rows_per_batch = (int)Lout, p.tiles_m_per_batch = (int)((Lout + 127) / 128);
     p.n_tiles = C / 256, p.umma_n = 256, p.block_k = bk, p.num_k_blocks = K / bk, p.kb_per_row = (2 * C) / bk;
     p.a_row_step = 1, p.a_row_off = 0, p.a_k_per_ntile = 0, p.b_n_tiled = 1, p.b_z_per_ntile = 0, p.b_k_linear = 1;
