@@ -75,7 +75,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
             )
             self.thread = threading.Thread(target=self._read, daemon=True)
@@ -85,11 +85,17 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.time()
 
     def stop(self):
+        """Summary of the samples taken between mark_begin() and now (the timed + profiled passes)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t1 = time.time()
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -97,7 +103,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if ts < getattr(self, "t0", 0.0) or ts > t1 + 0.03:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -236,22 +244,23 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     with torch.no_grad():
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        if sampler:
+            sampler.start()  # nvidia-smi needs ~100 ms to come up: start it before the warm-up
         for _ in range(max(args.warmup, 3)):
             step()
         # ---- timed region: device-resident inputs ----------------------------------------------------------
         native = expert._native
         launches0 = native.lib.s3b_launch_count(native.handle)
-        sampler = ClockSampler(local_rank) if rank == 0 else None
         barrier()
         if sampler:
-            sampler.start()
+            sampler.mark_begin()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
             step()
         e1.record()
         barrier()
-        clocks = sampler.stop() if sampler else None
         ms_total = torch.tensor([e0.elapsed_time(e1)], device=device)
         if world > 1:
             dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
@@ -270,6 +279,7 @@ def run_ours(args):
         ms5, fl5, ln5 = (C.c_double * 5)(), (C.c_double * 5)(), (C.c_int64 * 5)()
         s3lib.check(native.lib.s3b_profile_read(native.handle, ms5, fl5, ln5, 1))
         s3lib.check(native.lib.s3b_profile_enable(native.handle, 0))
+        clocks = sampler.stop() if sampler else None  # samples of the timed + profiled passes (same kernels, same load)
         cat = ["gemm_tcgen05", "attention_tcgen05", "conv0_norm_gelu", "layernorm", "misc"]
         breakdown = {c: {"ms_per_step": ms5[i] / args.steps, "launches_per_step": ln5[i] // args.steps,
                          "alg_tflop_per_step": fl5[i] / args.steps / 1e12} for i, c in enumerate(cat)}
@@ -337,7 +347,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
