@@ -307,7 +307,11 @@ static constexpr int k2StageBytes = 4 * k2TileBytes;      // A_hi A_lo B_hi B_lo
 static constexpr int k2Stages = 3;
 static constexpr int k2SmemBytes = k2Stages * k2StageBytes + 1024 + 256;
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+// 12 warps: TMA / MMA / TMEM-alloc / idle + EIGHT epilogue warps (two per TMEM lane quadrant, 128 columns each):
+// with four, the GELU + split epilogue of a K=768 tile (fc1, QKV) took longer than its 12 k-blocks of MMAs.
+static constexpr int k2Threads = 384;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
     gemm2_bf16x3_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -315,7 +319,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     uint64_t* full_bar = bars;                   // [k2Stages] used in the leader only (count 2 + tx bytes)
     uint64_t* empty_bar = bars + k2Stages;       // [k2Stages] one per CTA, multicast commit
     uint64_t* tmem_full = bars + 2 * k2Stages;   // [2]        one per CTA, multicast commit
-    uint64_t* tmem_empty = tmem_full + 2;        // [2]        leader only (8 epilogue warps)
+    uint64_t* tmem_empty = tmem_full + 2;        // [2]        leader only (16 epilogue warps of the pair)
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5;
@@ -337,7 +341,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], 8);  // 4 epilogue warps x 2 CTAs
+            mbar_init(&tmem_empty[s], 16);  // 8 epilogue warps x 2 CTAs
         }
         fence_mbar_init();
     }
@@ -426,7 +430,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         }
     } else if (warp >= 4) {
         // ===================== epilogue (both CTAs, 128 rows each) =====================
-        const int ew = warp - 4;
+        const int ew = (warp - 4) & 3;        // TMEM lane quadrant (== warp % 4)
+        const int chalf = (warp - 4) >> 2;    // which 128-column half of the accumulator this warp drains
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int pt = cluster_id; pt < num_pt; pt += num_clusters) {
@@ -444,7 +449,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             __syncwarp();
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * kAccCols;
-            for (int c = 0; c + 32 <= p.umma_n; c += 32) {
+            for (int c = chalf * 128; c < chalf * 128 + 128; c += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32(t_row + (uint32_t)c, v);
                 tmem_ld_wait();
@@ -480,7 +485,7 @@ static cudaError_t launch_pair(const GemmParams& p, int sm_count, cudaStream_t s
     const int num_pt = p.batches * ((p.tiles_m_per_batch + 1) / 2) * p.n_tiles;
     if (num_pt <= 0) return cudaSuccess;
     const int clusters = num_pt < sm_count / 2 ? num_pt : sm_count / 2;
-    gemm2_bf16x3_kernel<<<2 * clusters, kThreads, k2SmemBytes, stream>>>(p);
+    gemm2_bf16x3_kernel<<<2 * clusters, k2Threads, k2SmemBytes, stream>>>(p);
     return cudaGetLastError();
 }
 
