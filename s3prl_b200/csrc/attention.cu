@@ -10,8 +10,9 @@
 // softmax overlaps the other's MMAs. Per 64-key block j:
 //   S_j  = Qhi*Khi^T + Qhi*Klo^T + Qlo*Khi^T    tcgen05.mma M=128 N=64 K=64 -> TMEM cols [64*(j&1), +64)
 //   online softmax in fp32 registers (scores arrive in the log2 domain: q was scaled by log2(e)/8),
-//   P split to bf16 hi/lo -> 128B-swizzled smem, mbarrier hand-off to the control warp (no __syncthreads)
-//   PV_j = Phi*Vhi + Phi*Vlo + Plo*Vhi          tcgen05.mma M=128 N=64 K=64 -> TMEM cols [128, 192)
+//   P split to bf16 hi/lo -> TENSOR MEMORY (tcgen05.st, cols [192,224) / [224,256)), mbarrier hand-off to the
+//   control warp (no __syncthreads); P never touches shared memory: the N=64 MMAs are bound by smem bandwidth
+//   PV_j = Phi*Vhi + Phi*Vlo + Plo*Vhi          tcgen05.mma (A from TMEM) M=128 N=64 K=64 -> TMEM cols [128, 192)
 //   S_{j+1} is queued right behind PV_j (double-buffered S); O = O*alpha + PV_j in registers.
 // K and V^T have one smem buffer each: K_{j+1} is re-loaded as soon as S_j has retired, V_{j+1} as soon as PV_j has.
 #include <math.h>
@@ -26,15 +27,14 @@ static constexpr int kKBlk = 64;
 static constexpr int kHd = 64;
 static constexpr int kQBytes = kQTile * kHd * 2;    // 16 KB per plane
 static constexpr int kKBytes = kKBlk * kHd * 2;     // 8 KB per plane
-static constexpr int kPBytes = kQTile * kKBlk * 2;  // 16 KB per plane
-// smem map (1024-aligned): Qhi Qlo | Khi Klo | Vhi Vlo | Phi Plo | barriers
+// smem map (1024-aligned): Qhi Qlo | Khi Klo | Vhi Vlo | barriers
 static constexpr int kOffQ = 0;
 static constexpr int kOffK = 2 * kQBytes;
 static constexpr int kOffV = kOffK + 2 * kKBytes;
-static constexpr int kOffP = kOffV + 2 * kKBytes;
-static constexpr int kOffBar = kOffP + 2 * kPBytes;
-static constexpr int kAttnSmem = kOffBar + 128 + 1024;  // 99,456 B -> two CTAs per SM
-static constexpr int kTmemCols = 256;                    // S0 | S1 | PV | (unused)
+static constexpr int kOffBar = kOffV + 2 * kKBytes;
+static constexpr int kAttnSmem = kOffBar + 128 + 1024;  // 66,688 B; two CTAs per SM (TMEM: 2 x 256 columns)
+static constexpr int kTmemCols = 256;                    // S0 | S1 | PV | P_hi | P_lo
+static constexpr uint32_t kColPV = 128, kColPhi = 192, kColPlo = 224;
 static constexpr int kAttnThreads = 160;
 
 template <bool kBias>
@@ -84,18 +84,17 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_o = tmem_base + 128;
+    const uint32_t tmem_o = tmem_base + kColPV;
 
     if (warp == 4) {
         // ===================== control warp: TMA + MMA issue =====================
         if (elect_one()) {
             const uint32_t idesc = make_idesc_bf16(kQTile, 64);
             const uint32_t qa = smem_u32(smem + kOffQ), ka = smem_u32(smem + kOffK);
-            const uint32_t va = smem_u32(smem + kOffV), pa = smem_u32(smem + kOffP);
+            const uint32_t va = smem_u32(smem + kOffV);
             const uint64_t dq_hi = make_smem_desc_sw128(qa), dq_lo = make_smem_desc_sw128(qa + kQBytes);
             const uint64_t dk_hi = make_smem_desc_sw128(ka), dk_lo = make_smem_desc_sw128(ka + kKBytes);
             const uint64_t dv_hi = make_smem_desc_sw128(va), dv_lo = make_smem_desc_sw128(va + kKBytes);
-            const uint64_t dp_hi = make_smem_desc_sw128(pa), dp_lo = make_smem_desc_sw128(pa + kPBytes);
             auto load_k = [&](int j) {
                 mbar_arrive_expect_tx(bar_k, 2 * kKBytes);
                 tma_load_3d(smem + kOffK, &p.k_hi, bar_k, 0, j * kKBlk, bh);
@@ -136,9 +135,11 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
 #pragma unroll
                 for (int k = 0; k < kKBlk / 16; ++k) {
                     const uint64_t ko = (uint64_t)(2 * k);
-                    umma_bf16(tmem_o, dp_lo + ko, dv_hi + ko, idesc, k != 0 ? 1u : 0u);
-                    umma_bf16(tmem_o, dp_hi + ko, dv_lo + ko, idesc, 1u);
-                    umma_bf16(tmem_o, dp_hi + ko, dv_hi + ko, idesc, 1u);
+                    // 16 keys per MMA = 8 TMEM columns of packed bf16 pairs
+                    const uint32_t a_hi = tmem_base + kColPhi + 8u * k, a_lo = tmem_base + kColPlo + 8u * k;
+                    umma_bf16_ts(tmem_o, a_lo, dv_hi + ko, idesc, k != 0 ? 1u : 0u);
+                    umma_bf16_ts(tmem_o, a_hi, dv_lo + ko, idesc, 1u);
+                    umma_bf16_ts(tmem_o, a_hi, dv_hi + ko, idesc, 1u);
                 }
                 umma_commit(bar_pv);
                 if (more) {  // queue S_{j+1} right behind PV_j (its S buffer was consumed in iteration j-1)
@@ -166,11 +167,6 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
         for (int d = 0; d < kHd; ++d) o[d] = 0.f;
         float m_run = -INFINITY;  // running row max (log2 domain)
         float l_run = 0.f;
-        uint8_t* p_hi_s = smem + kOffP;
-        uint8_t* p_lo_s = smem + kOffP + kPBytes;
-        // 128B-swizzle placement of this thread's row inside a [128 x 64] bf16 K-major tile
-        const uint32_t row_off = (uint32_t)(tid >> 3) * 1024u + (uint32_t)(tid & 7) * 128u;
-        const uint32_t row_xor = (uint32_t)(tid & 7);
 
         for (int j = 0; j < nblk; ++j) {
             mbar_wait(&bar_s[j & 1], (uint32_t)((j >> 1) & 1));
@@ -206,24 +202,23 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
             const float alpha = fast_exp2(m_run - m_new);
             float psum0 = 0.f, psum1 = 0.f;
 #pragma unroll
-            for (int i = 0; i < kKBlk; i += 8) {
-                uint32_t hw[4], lw[4];
+            for (int half = 0; half < 2; ++half) {  // 32 keys = 16 packed columns per tcgen05.st
+                uint32_t hw[16], lw[16];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float p0 = fast_exp2(s[i + 2 * e] - m_new);
-                    const float p1 = fast_exp2(s[i + 2 * e + 1] - m_new);
+                for (int e = 0; e < 16; ++e) {
+                    const float p0 = fast_exp2(s[32 * half + 2 * e] - m_new);
+                    const float p1 = fast_exp2(s[32 * half + 2 * e + 1] - m_new);
                     psum0 += p0, psum1 += p1;
                     split_pack2(p0, p1, hw[e], lw[e]);
                 }
-                const uint32_t chunk = ((uint32_t)(i >> 3) ^ row_xor) * 16u;
-                *reinterpret_cast<uint4*>(p_hi_s + row_off + chunk) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                *reinterpret_cast<uint4*>(p_lo_s + row_off + chunk) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                tmem_st_32x16(tmem_base + lane_off + kColPhi + 16u * half, hw);
+                tmem_st_32x16(tmem_base + lane_off + kColPlo + 16u * half, lw);
             }
             l_run = fmaf(l_run, alpha, psum0 + psum1);
             m_run = m_new;
 
-            fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor-core async proxy
-            tc_fence_before();         // orders this thread's tcgen05.ld of S_j / PV_{j-1} before the hand-off
+            tmem_st_wait();     // P_j is in tensor memory
+            tc_fence_before();  // orders this thread's tcgen05.ld / tcgen05.st before the hand-off
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_p);
 
