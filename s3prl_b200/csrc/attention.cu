@@ -85,6 +85,11 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_o = tmem_base + kColPV;
+    const bool tracing = p.trace != nullptr && (int)blockIdx.x == p.trace_block;
+#define S3B_TR(role, j, slot)                                                                  \
+    do {                                                                                       \
+        if (tracing && (j) < 16) p.trace[((role)*16 + (j)) * 8 + (slot)] = clock64();          \
+    } while (0)
 
     if (warp == 4) {
         // ===================== control warp: TMA + MMA issue =====================
@@ -128,10 +133,13 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
             for (int j = 0; j < nblk; ++j) {
                 const bool more = j + 1 < nblk;
                 mbar_wait(&bar_s[j & 1], (uint32_t)((j >> 1) & 1));  // S_j retired: the K buffer is free
+                S3B_TR(0, j, 0);
                 if (more) load_k(j + 1);
-                mbar_wait(bar_p, (uint32_t)(j & 1));                  // P_j in smem, S_j consumed by every row
+                mbar_wait(bar_p, (uint32_t)(j & 1));                  // P_j in TMEM, S_j consumed by every row
+                S3B_TR(0, j, 1);
                 mbar_wait(bar_v, (uint32_t)(j & 1));
                 tc_fence_after();
+                S3B_TR(0, j, 2);
 #pragma unroll
                 for (int k = 0; k < kKBlk / 16; ++k) {
                     const uint64_t ko = (uint64_t)(2 * k);
@@ -142,12 +150,16 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
                     umma_bf16_ts(tmem_o, a_hi, dv_hi + ko, idesc, 1u);
                 }
                 umma_commit(bar_pv);
+                S3B_TR(0, j, 3);
                 if (more) {  // queue S_{j+1} right behind PV_j (its S buffer was consumed in iteration j-1)
                     mbar_wait(bar_k, (uint32_t)((j + 1) & 1));
                     tc_fence_after();
+                    S3B_TR(0, j, 4);
                     issue_s(j + 1);
+                    S3B_TR(0, j, 5);
                 }
                 mbar_wait(bar_pv, (uint32_t)(j & 1));  // PV_j retired: the V buffer is free
+                S3B_TR(0, j, 6);
                 if (more) load_v(j + 1);
             }
         }
@@ -172,6 +184,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
             mbar_wait(&bar_s[j & 1], (uint32_t)((j >> 1) & 1));
             __syncwarp();
             tc_fence_after();
+            if (tid == 0) S3B_TR(1, j, 0);
             float s[kKBlk];
             {
                 const uint32_t ts = tmem_base + (uint32_t)(j & 1) * 64u + lane_off;
@@ -182,6 +195,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
 #pragma unroll
                 for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(v0[i]), s[32 + i] = __uint_as_float(v1[i]);
             }
+            if (tid == 0) S3B_TR(1, j, 1);
             const int kbase = j * kKBlk;
             if (kBias) {
 #pragma unroll
@@ -217,14 +231,17 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
             l_run = fmaf(l_run, alpha, psum0 + psum1);
             m_run = m_new;
 
+            if (tid == 0) S3B_TR(1, j, 2);
             tmem_st_wait();     // P_j is in tensor memory
             tc_fence_before();  // orders this thread's tcgen05.ld / tcgen05.st before the hand-off
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_p);
+            if (tid == 0) S3B_TR(1, j, 3);
 
             mbar_wait(bar_pv, (uint32_t)(j & 1));
             __syncwarp();
             tc_fence_after();
+            if (tid == 0) S3B_TR(1, j, 4);
             {
                 uint32_t v0[32], v1[32];
                 tmem_ld_32x32(tmem_o + lane_off, v0);

@@ -42,6 +42,9 @@ struct AttnParams {
     const float* bias_table;    // [H][2T-1] or null
     const float* gate;          // [B][H][T] or null
     __nv_bfloat16 *ctx_hi, *ctx_lo;  // [B*T][D] split bf16 (A operand of out_proj)
+    // optional timeline (debug): clock64 stamps of CTA `trace_block`, [2 roles][16 blocks][8 slots]
+    long long* trace;
+    int trace_block;
 };
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t s);
 

@@ -993,7 +993,29 @@ extern "C" int s3b_attention_f32(const float* q, const float* k, const float* v,
     TMAP_OK(encode_tmap_bf16_3d(&ap.vt_lo, vts.l(), T, 64, BH, Tp, (uint64_t)64 * Tp, 64, 64));
     ap.B = B, ap.H = H, ap.T = T, ap.D = D, ap.kv_len = kv.as<int>();
     ap.ctx_hi = ctx.h(), ap.ctx_lo = ctx.l();
+    DevBuf trace;
+    const char* tb = getenv("S3B_ATTN_TRACE_BLOCK");  // debug: dump a clock64 timeline of one CTA to stderr
+    if (tb != nullptr) {
+        S3B_OK(trace.ensure(2 * 16 * 8 * sizeof(long long)));
+        CUDA_OK(cudaMemsetAsync(trace.p, 0, 2 * 16 * 8 * sizeof(long long), st));
+        ap.trace = trace.as<long long>(), ap.trace_block = atoi(tb);
+    }
     CUDA_OK(launch_attention(ap, st));
+    if (tb != nullptr) {
+        std::vector<long long> h(2 * 16 * 8);
+        CUDA_OK(cudaMemcpyAsync(h.data(), trace.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        long long t0 = 0;
+        for (long long v : h) if (v != 0 && (t0 == 0 || v < t0)) t0 = v;
+        for (int role = 0; role < 2; ++role)
+            for (int j = 0; j < 16; ++j) {
+                if (h[(role * 16 + j) * 8] == 0) continue;
+                fprintf(stderr, "attn-trace %s j=%2d:", role == 0 ? "ctrl" : "smax", j);
+                for (int sl = 0; sl < 8; ++sl) fprintf(stderr, " %7lld", h[(role * 16 + j) * 8 + sl] ? h[(role * 16 + j) * 8 + sl] - t0 : -1);
+                fprintf(stderr, "\n");
+            }
+        trace.release();
+    }
     CUDA_OK(launch_unsplit(ctx.h(), ctx.l(), M * D, out, st));
     cudaError_t se = cudaStreamSynchronize(st);
     qs.release(), ks.release(), vts.release(), ctx.release(), kv.release();
