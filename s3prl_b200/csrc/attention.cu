@@ -13,8 +13,9 @@
 //   P split to bf16 hi/lo -> TENSOR MEMORY (tcgen05.st, cols [192,224) / [224,256)), mbarrier hand-off to the
 //   control warp (no __syncthreads); P never touches shared memory: the N=64 MMAs are bound by smem bandwidth
 //   PV_j = Phi*Vhi + Phi*Vlo + Plo*Vhi          tcgen05.mma (A from TMEM) M=128 N=64 K=64 -> TMEM cols [128, 192)
-//   S_{j+1} is queued right behind PV_j (double-buffered S); O = O*alpha + PV_j in registers.
-// K and V^T have one smem buffer each: K_{j+1} is re-loaded as soon as S_j has retired, V_{j+1} as soon as PV_j has.
+//   O = O*alpha + PV_j in registers.
+// K / V^T blocks are double-buffered (block j+2 is fetched when PV_j has retired); S_{j+1} is issued BEFORE PV_j so
+// that it executes while the softmax warps are busy with S_j (measured timeline: tools/attn_trace.py).
 #include <math.h>
 
 #include "common.cuh"
@@ -27,12 +28,12 @@ static constexpr int kKBlk = 64;
 static constexpr int kHd = 64;
 static constexpr int kQBytes = kQTile * kHd * 2;    // 16 KB per plane
 static constexpr int kKBytes = kKBlk * kHd * 2;     // 8 KB per plane
-// smem map (1024-aligned): Qhi Qlo | Khi Klo | Vhi Vlo | barriers
+// smem map (1024-aligned): Qhi Qlo | 2 x {Khi Klo Vhi Vlo} | barriers
 static constexpr int kOffQ = 0;
-static constexpr int kOffK = 2 * kQBytes;
-static constexpr int kOffV = kOffK + 2 * kKBytes;
-static constexpr int kOffBar = kOffV + 2 * kKBytes;
-static constexpr int kAttnSmem = kOffBar + 128 + 1024;  // 66,688 B; two CTAs per SM (TMEM: 2 x 256 columns)
+static constexpr int kOffKV = 2 * kQBytes;
+static constexpr int kKVStage = 4 * kKBytes;
+static constexpr int kOffBar = kOffKV + 2 * kKVStage;
+static constexpr int kAttnSmem = kOffBar + 128 + 1024;  // 99,456 B; two CTAs per SM (TMEM: 2 x 256 columns)
 static constexpr int kTmemCols = 256;                    // S0 | S1 | PV | P_hi | P_lo
 static constexpr uint32_t kColPV = 128, kColPhi = 192, kColPlo = 224;
 static constexpr int kAttnThreads = 160;
@@ -42,8 +43,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + kOffBar);
-    uint64_t* bar_k = bar_q + 1;
-    uint64_t* bar_v = bar_q + 2;
+    uint64_t* bar_kv = bar_q + 1;  // [2]  K_j and V_j landed in stage j&1
     uint64_t* bar_s = bar_q + 3;   // [2]  S_j in TMEM (tcgen05.commit)
     uint64_t* bar_pv = bar_q + 5;  //      PV_j in TMEM (tcgen05.commit)
     uint64_t* bar_p = bar_q + 6;   //      P_j in smem and S_j consumed (one arrive per softmax warp)
@@ -62,8 +62,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
 
     if (tid == 0) {
         mbar_init(bar_q, 1);
-        mbar_init(bar_k, 1);
-        mbar_init(bar_v, 1);
+        mbar_init(&bar_kv[0], 1);
+        mbar_init(&bar_kv[1], 1);
         mbar_init(&bar_s[0], 1);
         mbar_init(&bar_s[1], 1);
         mbar_init(bar_pv, 1);
@@ -95,22 +95,20 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
         // ===================== control warp: TMA + MMA issue =====================
         if (elect_one()) {
             const uint32_t idesc = make_idesc_bf16(kQTile, 64);
-            const uint32_t qa = smem_u32(smem + kOffQ), ka = smem_u32(smem + kOffK);
-            const uint32_t va = smem_u32(smem + kOffV);
+            const uint32_t qa = smem_u32(smem + kOffQ), kva = smem_u32(smem + kOffKV);
             const uint64_t dq_hi = make_smem_desc_sw128(qa), dq_lo = make_smem_desc_sw128(qa + kQBytes);
-            const uint64_t dk_hi = make_smem_desc_sw128(ka), dk_lo = make_smem_desc_sw128(ka + kKBytes);
-            const uint64_t dv_hi = make_smem_desc_sw128(va), dv_lo = make_smem_desc_sw128(va + kKBytes);
-            auto load_k = [&](int j) {
-                mbar_arrive_expect_tx(bar_k, 2 * kKBytes);
-                tma_load_3d(smem + kOffK, &p.k_hi, bar_k, 0, j * kKBlk, bh);
-                tma_load_3d(smem + kOffK + kKBytes, &p.k_lo, bar_k, 0, j * kKBlk, bh);
-            };
-            auto load_v = [&](int j) {
-                mbar_arrive_expect_tx(bar_v, 2 * kKBytes);
-                tma_load_3d(smem + kOffV, &p.vt_hi, bar_v, j * kKBlk, 0, bh);
-                tma_load_3d(smem + kOffV + kKBytes, &p.vt_lo, bar_v, j * kKBlk, 0, bh);
+            auto load_kv = [&](int j) {  // K_j, V_j -> stage j&1, one barrier
+                uint8_t* st = smem + kOffKV + (j & 1) * kKVStage;
+                uint64_t* bar = &bar_kv[j & 1];
+                mbar_arrive_expect_tx(bar, 4 * kKBytes);
+                tma_load_3d(st, &p.k_hi, bar, 0, j * kKBlk, bh);
+                tma_load_3d(st + kKBytes, &p.k_lo, bar, 0, j * kKBlk, bh);
+                tma_load_3d(st + 2 * kKBytes, &p.vt_hi, bar, j * kKBlk, 0, bh);
+                tma_load_3d(st + 3 * kKBytes, &p.vt_lo, bar, j * kKBlk, 0, bh);
             };
             auto issue_s = [&](int j) {  // S_j = Q K_j^T into S buffer j&1
+                const uint32_t ka = kva + (uint32_t)(j & 1) * kKVStage;
+                const uint64_t dk_hi = make_smem_desc_sw128(ka), dk_lo = make_smem_desc_sw128(ka + kKBytes);
                 const uint32_t d = tmem_base + (uint32_t)(j & 1) * 64u;
 #pragma unroll
                 for (int k = 0; k < kHd / 16; ++k) {
@@ -124,22 +122,26 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
             mbar_arrive_expect_tx(bar_q, 2 * kQBytes);
             tma_load_3d(smem + kOffQ, &p.q_hi, bar_q, 0, q0, bh);
             tma_load_3d(smem + kOffQ + kQBytes, &p.q_lo, bar_q, 0, q0, bh);
-            load_k(0);
-            load_v(0);
+            load_kv(0);
+            if (nblk > 1) load_kv(1);
             mbar_wait(bar_q, 0);
-            mbar_wait(bar_k, 0);
+            mbar_wait(&bar_kv[0], 0);
             tc_fence_after();
             issue_s(0);
             for (int j = 0; j < nblk; ++j) {
                 const bool more = j + 1 < nblk;
-                mbar_wait(&bar_s[j & 1], (uint32_t)((j >> 1) & 1));  // S_j retired: the K buffer is free
                 S3B_TR(0, j, 0);
-                if (more) load_k(j + 1);
-                mbar_wait(bar_p, (uint32_t)(j & 1));                  // P_j in TMEM, S_j consumed by every row
+                if (more) {  // S_{j+1} runs on the tensor pipe while the softmax warps work on S_j
+                    mbar_wait(&bar_kv[(j + 1) & 1], (uint32_t)(((j + 1) >> 1) & 1));
+                    tc_fence_after();
+                    issue_s(j + 1);  // its S buffer was consumed before bar_p(j-1) completed
+                }
                 S3B_TR(0, j, 1);
-                mbar_wait(bar_v, (uint32_t)(j & 1));
+                mbar_wait(bar_p, (uint32_t)(j & 1));  // P_j in TMEM, S_j consumed by every row
                 tc_fence_after();
                 S3B_TR(0, j, 2);
+                const uint32_t va = kva + (uint32_t)(j & 1) * kKVStage + 2 * kKBytes;  // landed with K_j
+                const uint64_t dv_hi = make_smem_desc_sw128(va), dv_lo = make_smem_desc_sw128(va + kKBytes);
 #pragma unroll
                 for (int k = 0; k < kKBlk / 16; ++k) {
                     const uint64_t ko = (uint64_t)(2 * k);
@@ -151,16 +153,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
                 }
                 umma_commit(bar_pv);
                 S3B_TR(0, j, 3);
-                if (more) {  // queue S_{j+1} right behind PV_j (its S buffer was consumed in iteration j-1)
-                    mbar_wait(bar_k, (uint32_t)((j + 1) & 1));
-                    tc_fence_after();
-                    S3B_TR(0, j, 4);
-                    issue_s(j + 1);
-                    S3B_TR(0, j, 5);
-                }
-                mbar_wait(bar_pv, (uint32_t)(j & 1));  // PV_j retired: the V buffer is free
+                mbar_wait(bar_pv, (uint32_t)(j & 1));  // PV_j (and S_j) retired: stage j&1 is free
                 S3B_TR(0, j, 6);
-                if (more) load_v(j + 1);
+                if (j + 2 < nblk) load_kv(j + 2);
             }
         }
     } else {
