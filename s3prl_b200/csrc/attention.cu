@@ -14,7 +14,8 @@
 //   control warp (no __syncthreads); P never touches shared memory: the N=64 MMAs are bound by smem bandwidth
 //   PV_j = Phi*Vhi + Phi*Vlo + Plo*Vhi          tcgen05.mma (A from TMEM) M=128 N=64 K=64 -> TMEM cols [128, 192)
 //   O = O*alpha + PV_j in registers.
-// K / V^T blocks are double-buffered (block j+2 is fetched when PV_j has retired); S_{j+1} is issued BEFORE PV_j so
+// K and V^T blocks are double-buffered with separate barriers: K_{j+2} is fetched as soon as S_j has retired (two
+// blocks ahead; the measured TMA latency is ~2000 cycles), V_{j+2} when PV_j has. S_{j+1} is issued BEFORE PV_j so
 // that it executes while the softmax warps are busy with S_j (measured timeline: tools/attn_trace.py).
 #include <math.h>
 
@@ -28,11 +29,12 @@ static constexpr int kKBlk = 64;
 static constexpr int kHd = 64;
 static constexpr int kQBytes = kQTile * kHd * 2;    // 16 KB per plane
 static constexpr int kKBytes = kKBlk * kHd * 2;     // 8 KB per plane
-// smem map (1024-aligned): Qhi Qlo | 2 x {Khi Klo Vhi Vlo} | barriers
+// smem map (1024-aligned): Qhi Qlo | 2 x {Khi Klo} | 2 x {Vhi Vlo} | barriers
 static constexpr int kOffQ = 0;
-static constexpr int kOffKV = 2 * kQBytes;
-static constexpr int kKVStage = 4 * kKBytes;
-static constexpr int kOffBar = kOffKV + 2 * kKVStage;
+static constexpr int kOffK = 2 * kQBytes;
+static constexpr int kStage = 2 * kKBytes;  // one K (or V^T) block, hi + lo planes
+static constexpr int kOffV = kOffK + 2 * kStage;
+static constexpr int kOffBar = kOffV + 2 * kStage;
 static constexpr int kAttnSmem = kOffBar + 128 + 1024;  // 99,456 B; two CTAs per SM (TMEM: 2 x 256 columns)
 static constexpr int kTmemCols = 256;                    // S0 | S1 | PV | P_hi | P_lo
 static constexpr uint32_t kColPV = 128, kColPhi = 192, kColPlo = 224;
@@ -43,11 +45,12 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + kOffBar);
-    uint64_t* bar_kv = bar_q + 1;  // [2]  K_j and V_j landed in stage j&1
-    uint64_t* bar_s = bar_q + 3;   // [2]  S_j in TMEM (tcgen05.commit)
-    uint64_t* bar_pv = bar_q + 5;  //      PV_j in TMEM (tcgen05.commit)
-    uint64_t* bar_p = bar_q + 6;   //      P_j in smem and S_j consumed (one arrive per softmax warp)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 7);
+    uint64_t* bar_k = bar_q + 1;   // [2]  K_j landed in K stage j&1
+    uint64_t* bar_v = bar_q + 3;   // [2]  V_j landed in V stage j&1
+    uint64_t* bar_s = bar_q + 5;   // [2]  S_j in TMEM (tcgen05.commit)
+    uint64_t* bar_pv = bar_q + 7;  //      PV_j in TMEM (tcgen05.commit)
+    uint64_t* bar_p = bar_q + 8;   //      P_j in TMEM and S_j consumed (one arrive per softmax warp)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 9);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -62,8 +65,10 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
 
     if (tid == 0) {
         mbar_init(bar_q, 1);
-        mbar_init(&bar_kv[0], 1);
-        mbar_init(&bar_kv[1], 1);
+        mbar_init(&bar_k[0], 1);
+        mbar_init(&bar_k[1], 1);
+        mbar_init(&bar_v[0], 1);
+        mbar_init(&bar_v[1], 1);
         mbar_init(&bar_s[0], 1);
         mbar_init(&bar_s[1], 1);
         mbar_init(bar_pv, 1);
@@ -95,19 +100,22 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
         // ===================== control warp: TMA + MMA issue =====================
         if (elect_one()) {
             const uint32_t idesc = make_idesc_bf16(kQTile, 64);
-            const uint32_t qa = smem_u32(smem + kOffQ), kva = smem_u32(smem + kOffKV);
+            const uint32_t qa = smem_u32(smem + kOffQ);
             const uint64_t dq_hi = make_smem_desc_sw128(qa), dq_lo = make_smem_desc_sw128(qa + kQBytes);
-            auto load_kv = [&](int j) {  // K_j, V_j -> stage j&1, one barrier
-                uint8_t* st = smem + kOffKV + (j & 1) * kKVStage;
-                uint64_t* bar = &bar_kv[j & 1];
-                mbar_arrive_expect_tx(bar, 4 * kKBytes);
-                tma_load_3d(st, &p.k_hi, bar, 0, j * kKBlk, bh);
-                tma_load_3d(st + kKBytes, &p.k_lo, bar, 0, j * kKBlk, bh);
-                tma_load_3d(st + 2 * kKBytes, &p.vt_hi, bar, j * kKBlk, 0, bh);
-                tma_load_3d(st + 3 * kKBytes, &p.vt_lo, bar, j * kKBlk, 0, bh);
+            auto load_k = [&](int j) {  // K_j -> K stage j&1
+                uint8_t* st = smem + kOffK + (j & 1) * kStage;
+                mbar_arrive_expect_tx(&bar_k[j & 1], 2 * kKBytes);
+                tma_load_3d(st, &p.k_hi, &bar_k[j & 1], 0, j * kKBlk, bh);
+                tma_load_3d(st + kKBytes, &p.k_lo, &bar_k[j & 1], 0, j * kKBlk, bh);
+            };
+            auto load_v = [&](int j) {  // V^T_j -> V stage j&1
+                uint8_t* st = smem + kOffV + (j & 1) * kStage;
+                mbar_arrive_expect_tx(&bar_v[j & 1], 2 * kKBytes);
+                tma_load_3d(st, &p.vt_hi, &bar_v[j & 1], j * kKBlk, 0, bh);
+                tma_load_3d(st + kKBytes, &p.vt_lo, &bar_v[j & 1], j * kKBlk, 0, bh);
             };
             auto issue_s = [&](int j) {  // S_j = Q K_j^T into S buffer j&1
-                const uint32_t ka = kva + (uint32_t)(j & 1) * kKVStage;
+                const uint32_t ka = smem_u32(smem + kOffK + (j & 1) * kStage);
                 const uint64_t dk_hi = make_smem_desc_sw128(ka), dk_lo = make_smem_desc_sw128(ka + kKBytes);
                 const uint32_t d = tmem_base + (uint32_t)(j & 1) * 64u;
 #pragma unroll
@@ -122,25 +130,32 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
             mbar_arrive_expect_tx(bar_q, 2 * kQBytes);
             tma_load_3d(smem + kOffQ, &p.q_hi, bar_q, 0, q0, bh);
             tma_load_3d(smem + kOffQ + kQBytes, &p.q_lo, bar_q, 0, q0, bh);
-            load_kv(0);
-            if (nblk > 1) load_kv(1);
+            load_k(0);
+            load_v(0);
+            if (nblk > 1) load_k(1), load_v(1);
             mbar_wait(bar_q, 0);
-            mbar_wait(&bar_kv[0], 0);
+            mbar_wait(&bar_k[0], 0);
             tc_fence_after();
             issue_s(0);
+            mbar_wait(&bar_s[0], 0);  // S_0 retired: K stage 0 is free again
+            if (nblk > 2) load_k(2);
             for (int j = 0; j < nblk; ++j) {
                 const bool more = j + 1 < nblk;
                 S3B_TR(0, j, 0);
                 if (more) {  // S_{j+1} runs on the tensor pipe while the softmax warps work on S_j
-                    mbar_wait(&bar_kv[(j + 1) & 1], (uint32_t)(((j + 1) >> 1) & 1));
+                    mbar_wait(&bar_k[(j + 1) & 1], (uint32_t)(((j + 1) >> 1) & 1));
                     tc_fence_after();
                     issue_s(j + 1);  // its S buffer was consumed before bar_p(j-1) completed
+                    // K loads run two blocks ahead (TMA latency ~2000 cycles, measured): K_{j+3} replaces K_{j+1}
+                    mbar_wait(&bar_s[(j + 1) & 1], (uint32_t)(((j + 1) >> 1) & 1));
+                    if (j + 3 < nblk) load_k(j + 3);
                 }
                 S3B_TR(0, j, 1);
                 mbar_wait(bar_p, (uint32_t)(j & 1));  // P_j in TMEM, S_j consumed by every row
+                mbar_wait(&bar_v[j & 1], (uint32_t)((j >> 1) & 1));
                 tc_fence_after();
                 S3B_TR(0, j, 2);
-                const uint32_t va = kva + (uint32_t)(j & 1) * kKVStage + 2 * kKBytes;  // landed with K_j
+                const uint32_t va = smem_u32(smem + kOffV + (j & 1) * kStage);
                 const uint64_t dv_hi = make_smem_desc_sw128(va), dv_lo = make_smem_desc_sw128(va + kKBytes);
 #pragma unroll
                 for (int k = 0; k < kKBlk / 16; ++k) {
@@ -153,9 +168,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
                 }
                 umma_commit(bar_pv);
                 S3B_TR(0, j, 3);
-                mbar_wait(bar_pv, (uint32_t)(j & 1));  // PV_j (and S_j) retired: stage j&1 is free
+                mbar_wait(bar_pv, (uint32_t)(j & 1));  // PV_j retired: V stage j&1 is free
                 S3B_TR(0, j, 6);
-                if (j + 2 < nblk) load_kv(j + 2);
+                if (j + 2 < nblk) load_v(j + 2);
             }
         }
     } else {
