@@ -5,18 +5,17 @@
 //
 // One CTA = one (batch, head, 128-query tile), 160 threads:
 //   warps 0..3 : softmax warps, thread i owns query row i (TMEM lane i)
-//   warp 4     : control warp (lane 0): TMA loads and every tcgen05.mma / commit
-// Two CTAs are co-resident per SM (<= 204 registers/thread, ~97 KB smem, 256 TMEM columns each), so one CTA's
-// softmax overlaps the other's MMAs. Per 64-key block j:
-//   S_j  = Qhi*Khi^T + Qhi*Klo^T + Qlo*Khi^T    tcgen05.mma M=128 N=64 K=64 -> TMEM cols [64*(j&1), +64)
-//   online softmax in fp32 registers (scores arrive in the log2 domain: q was scaled by log2(e)/8),
-//   P split to bf16 hi/lo -> TENSOR MEMORY (tcgen05.st, cols [192,224) / [224,256)), mbarrier hand-off to the
-//   control warp (no __syncthreads); P never touches shared memory: the N=64 MMAs are bound by smem bandwidth
-//   PV_j = Phi*Vhi + Phi*Vlo + Plo*Vhi          tcgen05.mma (A from TMEM) M=128 N=64 K=64 -> TMEM cols [128, 192)
-//   O = O*alpha + PV_j in registers.
-// K and V^T blocks are double-buffered with separate barriers: K_{j+2} is fetched as soon as S_j has retired (two
-// blocks ahead; the measured TMA latency is ~2000 cycles), V_{j+2} when PV_j has. S_{j+1} is issued BEFORE PV_j so
-// that it executes while the softmax warps are busy with S_j (measured timeline: tools/attn_trace.py).
+//   warp 4     : control warp (one elected lane): TMA loads and every tcgen05.mma / commit
+// Two CTAs are co-resident per SM (<= 204 registers/thread, ~97 KB smem, 256 TMEM columns each).
+// TMEM columns: S0 [0,64) | S1 [64,128) | O [128,192) | P_hi [192,224) | P_lo [224,256).
+// Per 64-key block j:
+//   S_j = Qhi*Khi^T + Qhi*Klo^T + Qlo*Khi^T     tcgen05.mma M=128 N=64 K=64, issued one block ahead
+//   softmax warps: scores (log2 domain: q was scaled by log2(e)/8) -> running max m, p = 2^(s-m), split to
+//     bf16 hi/lo and stored to TENSOR MEMORY (tcgen05.st); if any row's max moved, O (which lives in TMEM) is
+//     rescaled by alpha with tcgen05.ld / tcgen05.st — only after PV_{j-1} has retired, which it has long before
+//   O += Phi*Vhi + Phi*Vlo + Plo*Vhi            tcgen05.mma with A from TMEM, accumulating across blocks
+// The softmax warps never wait for PV_j inside the loop, so the tensor pipe, the MUFU pipe and TMA overlap
+// (timeline: tools/attn_trace.py). K^T/V blocks: double-buffered, K two blocks ahead (TMA latency ~2000 cycles).
 #include <math.h>
 
 #include "common.cuh"
@@ -27,8 +26,8 @@ namespace s3b {
 static constexpr int kQTile = 128;
 static constexpr int kKBlk = 64;
 static constexpr int kHd = 64;
-static constexpr int kQBytes = kQTile * kHd * 2;    // 16 KB per plane
-static constexpr int kKBytes = kKBlk * kHd * 2;     // 8 KB per plane
+static constexpr int kQBytes = kQTile * kHd * 2;  // 16 KB per plane
+static constexpr int kKBytes = kKBlk * kHd * 2;   // 8 KB per plane
 // smem map (1024-aligned): Qhi Qlo | 2 x {Khi Klo} | 2 x {Vhi Vlo} | barriers
 static constexpr int kOffQ = 0;
 static constexpr int kOffK = 2 * kQBytes;
@@ -36,8 +35,8 @@ static constexpr int kStage = 2 * kKBytes;  // one K (or V^T) block, hi + lo pla
 static constexpr int kOffV = kOffK + 2 * kStage;
 static constexpr int kOffBar = kOffV + 2 * kStage;
 static constexpr int kAttnSmem = kOffBar + 128 + 1024;  // 99,456 B; two CTAs per SM (TMEM: 2 x 256 columns)
-static constexpr int kTmemCols = 256;                    // S0 | S1 | PV | P_hi | P_lo
-static constexpr uint32_t kColPV = 128, kColPhi = 192, kColPlo = 224;
+static constexpr int kTmemCols = 256;
+static constexpr uint32_t kColO = 128, kColPhi = 192, kColPlo = 224;
 static constexpr int kAttnThreads = 160;
 
 template <bool kBias>
@@ -48,8 +47,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
     uint64_t* bar_k = bar_q + 1;   // [2]  K_j landed in K stage j&1
     uint64_t* bar_v = bar_q + 3;   // [2]  V_j landed in V stage j&1
     uint64_t* bar_s = bar_q + 5;   // [2]  S_j in TMEM (tcgen05.commit)
-    uint64_t* bar_pv = bar_q + 7;  //      PV_j in TMEM (tcgen05.commit)
-    uint64_t* bar_p = bar_q + 8;   //      P_j in TMEM and S_j consumed (one arrive per softmax warp)
+    uint64_t* bar_pv = bar_q + 7;  //      O += P_j V_j retired (tcgen05.commit)
+    uint64_t* bar_p = bar_q + 8;   //      P_j in TMEM, O rescaled, S_j consumed (one arrive per softmax warp)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 9);
 
     const int tid = threadIdx.x;
@@ -89,11 +88,11 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_o = tmem_base + kColPV;
+    const uint32_t tmem_o = tmem_base + kColO;
     const bool tracing = p.trace != nullptr && (int)blockIdx.x == p.trace_block;
-#define S3B_TR(role, j, slot)                                                                  \
-    do {                                                                                       \
-        if (tracing && (j) < 16) p.trace[((role)*16 + (j)) * 8 + (slot)] = clock64();          \
+#define S3B_TR(role, j, slot)                                                         \
+    do {                                                                              \
+        if (tracing && (j) < 16) p.trace[((role)*16 + (j)) * 8 + (slot)] = clock64(); \
     } while (0)
 
     if (warp == 4) {
@@ -137,8 +136,6 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
             mbar_wait(&bar_k[0], 0);
             tc_fence_after();
             issue_s(0);
-            mbar_wait(&bar_s[0], 0);  // S_0 retired: K stage 0 is free again
-            if (nblk > 2) load_k(2);
             for (int j = 0; j < nblk; ++j) {
                 const bool more = j + 1 < nblk;
                 S3B_TR(0, j, 0);
@@ -146,13 +143,14 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
                     mbar_wait(&bar_k[(j + 1) & 1], (uint32_t)(((j + 1) >> 1) & 1));
                     tc_fence_after();
                     issue_s(j + 1);  // its S buffer was consumed before bar_p(j-1) completed
-                    // K loads run two blocks ahead (TMA latency ~2000 cycles, measured): K_{j+3} replaces K_{j+1}
-                    mbar_wait(&bar_s[(j + 1) & 1], (uint32_t)(((j + 1) >> 1) & 1));
-                    if (j + 3 < nblk) load_k(j + 3);
                 }
+                if (j >= 1) {  // PV_{j-1} retired (it was issued a whole softmax phase ago): refill its V stage
+                    mbar_wait(bar_pv, (uint32_t)((j - 1) & 1));
+                    if (j + 1 < nblk) load_v(j + 1);
+                }
+                mbar_wait(&bar_v[j & 1], (uint32_t)((j >> 1) & 1));  // off the critical path: V_j landed long ago
                 S3B_TR(0, j, 1);
-                mbar_wait(bar_p, (uint32_t)(j & 1));  // P_j in TMEM, S_j consumed by every row
-                mbar_wait(&bar_v[j & 1], (uint32_t)((j >> 1) & 1));
+                mbar_wait(bar_p, (uint32_t)(j & 1));  // P_j in TMEM, O rescaled, S_j consumed by every row
                 tc_fence_after();
                 S3B_TR(0, j, 2);
                 const uint32_t va = smem_u32(smem + kOffV + (j & 1) * kStage);
@@ -162,15 +160,17 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
                     const uint64_t ko = (uint64_t)(2 * k);
                     // 16 keys per MMA = 8 TMEM columns of packed bf16 pairs
                     const uint32_t a_hi = tmem_base + kColPhi + 8u * k, a_lo = tmem_base + kColPlo + 8u * k;
-                    umma_bf16_ts(tmem_o, a_lo, dv_hi + ko, idesc, k != 0 ? 1u : 0u);
+                    umma_bf16_ts(tmem_o, a_lo, dv_hi + ko, idesc, (j | k) != 0 ? 1u : 0u);
                     umma_bf16_ts(tmem_o, a_hi, dv_lo + ko, idesc, 1u);
                     umma_bf16_ts(tmem_o, a_hi, dv_hi + ko, idesc, 1u);
                 }
                 umma_commit(bar_pv);
                 S3B_TR(0, j, 3);
-                mbar_wait(bar_pv, (uint32_t)(j & 1));  // PV_j retired: V stage j&1 is free
-                S3B_TR(0, j, 6);
-                if (j + 2 < nblk) load_v(j + 2);
+                if (more) {  // K runs two blocks ahead: K_{j+3} replaces K_{j+1} once S_{j+1} has retired
+                    mbar_wait(&bar_s[(j + 1) & 1], (uint32_t)(((j + 1) >> 1) & 1));
+                    if (j + 3 < nblk) load_k(j + 3);
+                }
+                S3B_TR(0, j, 4);
             }
         }
     } else {
@@ -184,9 +184,6 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
             gate = (p.gate == nullptr) ? 1.0f : (row_ok ? p.gate[((size_t)b * p.H + h) * p.T + q_row] : 0.f);
             brow = p.bias_table + (size_t)h * (2 * p.T - 1) + (p.T - 1 - (row_ok ? q_row : 0));  // index by key k
         }
-        float o[kHd];
-#pragma unroll
-        for (int d = 0; d < kHd; ++d) o[d] = 0.f;
         float m_run = -INFINITY;  // running row max (log2 domain)
         float l_run = 0.f;
 
@@ -205,7 +202,6 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
 #pragma unroll
                 for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(v0[i]), s[32 + i] = __uint_as_float(v1[i]);
             }
-            if (tid == 0) S3B_TR(1, j, 1);
             const int kbase = j * kKBlk;
             if (kBias) {
 #pragma unroll
@@ -225,58 +221,69 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
             const float m_new = fmaxf(m_run, mx);  // finite: key kbase is always valid
             const float alpha = fast_exp2(m_run - m_new);
             float psum0 = 0.f, psum1 = 0.f;
+            uint32_t hw[32], lw[32];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {  // 32 keys = 16 packed columns per tcgen05.st
-                uint32_t hw[16], lw[16];
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const float p0 = fast_exp2(s[32 * half + 2 * e] - m_new);
-                    const float p1 = fast_exp2(s[32 * half + 2 * e + 1] - m_new);
-                    psum0 += p0, psum1 += p1;
-                    split_pack2(p0, p1, hw[e], lw[e]);
-                }
-                tmem_st_32x16(tmem_base + lane_off + kColPhi + 16u * half, hw);
-                tmem_st_32x16(tmem_base + lane_off + kColPlo + 16u * half, lw);
+            for (int e = 0; e < 32; ++e) {
+                const float p0 = fast_exp2(s[2 * e] - m_new);
+                const float p1 = fast_exp2(s[2 * e + 1] - m_new);
+                psum0 += p0, psum1 += p1;
+                split_pack2(p0, p1, hw[e], lw[e]);
             }
             l_run = fmaf(l_run, alpha, psum0 + psum1);
             m_run = m_new;
+            if (tid == 0) S3B_TR(1, j, 1);
 
-            if (tid == 0) S3B_TR(1, j, 2);
-            tmem_st_wait();     // P_j is in tensor memory
+            if (j > 0) {
+                // P_{j-1} and O are still owned by PV_{j-1} until it retires (issued ~one softmax phase ago)
+                mbar_wait(bar_pv, (uint32_t)((j - 1) & 1));
+                __syncwarp();
+                tc_fence_after();
+                if (tid == 0) S3B_TR(1, j, 2);
+                if (!__all_sync(0xffffffffu, alpha == 1.0f)) {  // some row's max moved: rescale O in place
+#pragma unroll
+                    for (int c = 0; c < kHd; c += 32) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(tmem_o + lane_off + (uint32_t)c, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                        tmem_st_32x32(tmem_o + lane_off + (uint32_t)c, v);
+                    }
+                }
+            }
+            tmem_st_32x32(tmem_base + lane_off + kColPhi, hw);
+            tmem_st_32x32(tmem_base + lane_off + kColPlo, lw);
+            tmem_st_wait();     // P_j and the rescaled O are in tensor memory
             tc_fence_before();  // orders this thread's tcgen05.ld / tcgen05.st before the hand-off
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_p);
             if (tid == 0) S3B_TR(1, j, 3);
-
-            mbar_wait(bar_pv, (uint32_t)(j & 1));
-            __syncwarp();
-            tc_fence_after();
-            if (tid == 0) S3B_TR(1, j, 4);
-            {
-                uint32_t v0[32], v1[32];
-                tmem_ld_32x32(tmem_o + lane_off, v0);
-                tmem_ld_32x32(tmem_o + lane_off + 32, v1);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    o[i] = fmaf(o[i], alpha, __uint_as_float(v0[i]));
-                    o[32 + i] = fmaf(o[32 + i], alpha, __uint_as_float(v1[i]));
-                }
-            }
         }
 
-        if (row_ok) {
-            const float inv = 1.0f / l_run;
-            const size_t off = ((size_t)b * p.T + q_row) * (size_t)p.D + (size_t)h * kHd;
-            uint4* dh = reinterpret_cast<uint4*>(p.ctx_hi + off);
-            uint4* dl = reinterpret_cast<uint4*>(p.ctx_lo + off);
+        // O is complete once the last PV has retired
+        mbar_wait(bar_pv, (uint32_t)((nblk - 1) & 1));
+        __syncwarp();
+        tc_fence_after();
+        const float inv = 1.0f / l_run;
+        const size_t off = ((size_t)b * p.T + (row_ok ? q_row : 0)) * (size_t)p.D + (size_t)h * kHd;
 #pragma unroll
-            for (int i = 0; i < kHd; i += 8) {
-                uint32_t hw[4], lw[4];
+        for (int c = 0; c < kHd; c += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_o + lane_off + (uint32_t)c, v);
+            tmem_ld_wait();
+            if (row_ok) {
+                uint4* dh = reinterpret_cast<uint4*>(p.ctx_hi + off + c);
+                uint4* dl = reinterpret_cast<uint4*>(p.ctx_lo + off + c);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) split_pack2(o[i + 2 * e] * inv, o[i + 2 * e + 1] * inv, hw[e], lw[e]);
-                dh[i >> 3] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                dl[i >> 3] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                for (int i = 0; i < 32; i += 8) {
+                    uint32_t hw[4], lw[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        split_pack2(__uint_as_float(v[i + 2 * e]) * inv, __uint_as_float(v[i + 2 * e + 1]) * inv, hw[e],
+                                    lw[e]);
+                    dh[i >> 3] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    dl[i >> 3] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                }
             }
         }
     }
