@@ -136,6 +136,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
             mbar_wait(&bar_k[0], 0);
             tc_fence_after();
             issue_s(0);
+            mbar_wait(&bar_s[0], 0);  // S_0 retired: K stage 0 is free again
+            if (nblk > 2) load_k(2);
             for (int j = 0; j < nblk; ++j) {
                 const bool more = j + 1 < nblk;
                 S3B_TR(0, j, 0);
