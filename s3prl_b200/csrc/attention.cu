@@ -3,13 +3,15 @@
 // (s3prl/upstream/wav2vec2/wav2vec2_model.py:1146-1168) and, when bias_table is given, WavLM's gated
 // relative-position bias (s3prl/upstream/wavlm/modules.py:511-580).
 //
-// One CTA = one (batch, head, 128-query tile), 160 threads:
+// One CTA = one (batch, head, 128-query tile), 192 threads:
 //   warps 0..3 : softmax warps, thread i owns query row i (TMEM lane i)
-//   warp 4     : control warp (one elected lane): TMA loads and every tcgen05.mma / commit
-// Two CTAs are co-resident per SM (<= 204 registers/thread, ~97 KB smem, 256 TMEM columns each).
+//   warp 4     : S warp  (one elected lane): Q/K TMA loads, S_j = Q K_j^T
+//   warp 5     : PV warp (one elected lane): V TMA loads, O += P_j V_j
+//   (one control warp doing both serialised ~2400 cycles of barrier waits + MMA issue per block)
+// Two CTAs are co-resident per SM (<= 168 registers/thread, ~97 KB smem, 256 TMEM columns each).
 // TMEM columns: S0 [0,64) | S1 [64,128) | O [128,192) | P_hi [192,224) | P_lo [224,256).
 // Per 64-key block j:
-//   S_j = Qhi*Khi^T + Qhi*Klo^T + Qlo*Khi^T     tcgen05.mma M=128 N=64 K=64, issued one block ahead
+//   S_j = Qhi*Khi^T + Qhi*Klo^T + Qlo*Khi^T     tcgen05.mma M=128 N=64 K=64, as soon as its S buffer is free
 //   softmax warps: scores (log2 domain: q was scaled by log2(e)/8) -> running max m, p = 2^(s-m), split to
 //     bf16 hi/lo and stored to TENSOR MEMORY (tcgen05.st); if any row's max moved, O (which lives in TMEM) is
 //     rescaled by alpha with tcgen05.ld / tcgen05.st — only after PV_{j-1} has retired, which it has long before
@@ -37,7 +39,7 @@ static constexpr int kOffBar = kOffV + 2 * kStage;
 static constexpr int kAttnSmem = kOffBar + 128 + 1024;  // 99,456 B; two CTAs per SM (TMEM: 2 x 256 columns)
 static constexpr int kTmemCols = 256;
 static constexpr uint32_t kColO = 128, kColPhi = 192, kColPlo = 224;
-static constexpr int kAttnThreads = 160;
+static constexpr int kAttnThreads = 192;
 
 template <bool kBias>
 __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid_constant__ AttnParams p) {
@@ -49,7 +51,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
     uint64_t* bar_s = bar_q + 5;   // [2]  S_j in TMEM (tcgen05.commit)
     uint64_t* bar_pv = bar_q + 7;  //      O += P_j V_j retired (tcgen05.commit)
     uint64_t* bar_p = bar_q + 8;   //      P_j in TMEM, O rescaled, S_j consumed (one arrive per softmax warp)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 9);
+    uint64_t* bar_sfree = bar_q + 9;  // [2] S buffer j&1 has been read into registers by every row (4 warp arrives)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 11);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -72,6 +75,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
         mbar_init(&bar_s[1], 1);
         mbar_init(bar_pv, 1);
         mbar_init(bar_p, 4);
+        mbar_init(&bar_sfree[0], 4);
+        mbar_init(&bar_sfree[1], 4);
         fence_mbar_init();
     }
     if (warp == 4) {
@@ -96,7 +101,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
     } while (0)
 
     if (warp == 4) {
-        // ===================== control warp: TMA + MMA issue =====================
+        // ===================== S warp: Q/K loads + S_j = Q K_j^T =====================
         if (elect_one()) {
             const uint32_t idesc = make_idesc_bf16(kQTile, 64);
             const uint32_t qa = smem_u32(smem + kOffQ);
@@ -107,13 +112,19 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
                 tma_load_3d(st, &p.k_hi, &bar_k[j & 1], 0, j * kKBlk, bh);
                 tma_load_3d(st + kKBytes, &p.k_lo, &bar_k[j & 1], 0, j * kKBlk, bh);
             };
-            auto load_v = [&](int j) {  // V^T_j -> V stage j&1
-                uint8_t* st = smem + kOffV + (j & 1) * kStage;
-                mbar_arrive_expect_tx(&bar_v[j & 1], 2 * kKBytes);
-                tma_load_3d(st, &p.vt_hi, &bar_v[j & 1], j * kKBlk, 0, bh);
-                tma_load_3d(st + kKBytes, &p.vt_lo, &bar_v[j & 1], j * kKBlk, 0, bh);
-            };
-            auto issue_s = [&](int j) {  // S_j = Q K_j^T into S buffer j&1
+            mbar_arrive_expect_tx(bar_q, 2 * kQBytes);
+            tma_load_3d(smem + kOffQ, &p.q_hi, bar_q, 0, q0, bh);
+            tma_load_3d(smem + kOffQ + kQBytes, &p.q_lo, bar_q, 0, q0, bh);
+            load_k(0);
+            if (nblk > 1) load_k(1);
+            mbar_wait(bar_q, 0);
+            for (int j = 0; j < nblk; ++j) {
+                S3B_TR(0, j, 0);
+                mbar_wait(&bar_k[j & 1], (uint32_t)((j >> 1) & 1));
+                // S buffer j&1 is free once every row has read S_{j-2} into registers
+                if (j >= 2) mbar_wait(&bar_sfree[j & 1], (uint32_t)(((j >> 1) - 1) & 1));
+                tc_fence_after();
+                S3B_TR(0, j, 1);
                 const uint32_t ka = smem_u32(smem + kOffK + (j & 1) * kStage);
                 const uint64_t dk_hi = make_smem_desc_sw128(ka), dk_lo = make_smem_desc_sw128(ka + kKBytes);
                 const uint32_t d = tmem_base + (uint32_t)(j & 1) * 64u;
@@ -125,36 +136,32 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
                     umma_bf16(d, dq_hi + ko, dk_hi + ko, idesc, 1u);
                 }
                 umma_commit(&bar_s[j & 1]);
+                S3B_TR(0, j, 2);
+                if (j + 2 < nblk) {  // K_{j+2} replaces K_j as soon as S_j has retired
+                    mbar_wait(&bar_s[j & 1], (uint32_t)((j >> 1) & 1));
+                    load_k(j + 2);
+                }
+                S3B_TR(0, j, 3);
+            }
+        }
+    } else if (warp == 5) {
+        // ===================== PV warp: V loads + O += P_j V_j =====================
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_bf16(kQTile, 64);
+            auto load_v = [&](int j) {  // V^T_j -> V stage j&1
+                uint8_t* st = smem + kOffV + (j & 1) * kStage;
+                mbar_arrive_expect_tx(&bar_v[j & 1], 2 * kKBytes);
+                tma_load_3d(st, &p.vt_hi, &bar_v[j & 1], j * kKBlk, 0, bh);
+                tma_load_3d(st + kKBytes, &p.vt_lo, &bar_v[j & 1], j * kKBlk, 0, bh);
             };
-            mbar_arrive_expect_tx(bar_q, 2 * kQBytes);
-            tma_load_3d(smem + kOffQ, &p.q_hi, bar_q, 0, q0, bh);
-            tma_load_3d(smem + kOffQ + kQBytes, &p.q_lo, bar_q, 0, q0, bh);
-            load_k(0);
             load_v(0);
-            if (nblk > 1) load_k(1), load_v(1);
-            mbar_wait(bar_q, 0);
-            mbar_wait(&bar_k[0], 0);
-            tc_fence_after();
-            issue_s(0);
-            mbar_wait(&bar_s[0], 0);  // S_0 retired: K stage 0 is free again
-            if (nblk > 2) load_k(2);
+            if (nblk > 1) load_v(1);
             for (int j = 0; j < nblk; ++j) {
-                const bool more = j + 1 < nblk;
-                S3B_TR(0, j, 0);
-                if (more) {  // S_{j+1} runs on the tensor pipe while the softmax warps work on S_j
-                    mbar_wait(&bar_k[(j + 1) & 1], (uint32_t)(((j + 1) >> 1) & 1));
-                    tc_fence_after();
-                    issue_s(j + 1);  // its S buffer was consumed before bar_p(j-1) completed
-                }
-                if (j >= 1) {  // PV_{j-1} retired (it was issued a whole softmax phase ago): refill its V stage
-                    mbar_wait(bar_pv, (uint32_t)((j - 1) & 1));
-                    if (j + 1 < nblk) load_v(j + 1);
-                }
-                mbar_wait(&bar_v[j & 1], (uint32_t)((j >> 1) & 1));  // off the critical path: V_j landed long ago
-                S3B_TR(0, j, 1);
+                mbar_wait(&bar_v[j & 1], (uint32_t)((j >> 1) & 1));  // V_j landed long ago
+                S3B_TR(0, j, 4);
                 mbar_wait(bar_p, (uint32_t)(j & 1));  // P_j in TMEM, O rescaled, S_j consumed by every row
                 tc_fence_after();
-                S3B_TR(0, j, 2);
+                S3B_TR(0, j, 5);
                 const uint32_t va = smem_u32(smem + kOffV + (j & 1) * kStage);
                 const uint64_t dv_hi = make_smem_desc_sw128(va), dv_lo = make_smem_desc_sw128(va + kKBytes);
 #pragma unroll
@@ -167,12 +174,11 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
                     umma_bf16_ts(tmem_o, a_hi, dv_hi + ko, idesc, 1u);
                 }
                 umma_commit(bar_pv);
-                S3B_TR(0, j, 3);
-                if (more) {  // K runs two blocks ahead: K_{j+3} replaces K_{j+1} once S_{j+1} has retired
-                    mbar_wait(&bar_s[(j + 1) & 1], (uint32_t)(((j + 1) >> 1) & 1));
-                    if (j + 3 < nblk) load_k(j + 3);
+                S3B_TR(0, j, 6);
+                if (j + 2 < nblk) {  // V_{j+2} replaces V_j once PV_j has retired
+                    mbar_wait(bar_pv, (uint32_t)(j & 1));
+                    load_v(j + 2);
                 }
-                S3B_TR(0, j, 4);
             }
         }
     } else {
@@ -204,6 +210,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
 #pragma unroll
                 for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(v0[i]), s[32 + i] = __uint_as_float(v1[i]);
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_sfree[j & 1]);  // the S warp may overwrite this buffer with S_{j+2}
             const int kbase = j * kKBlk;
             if (kBias) {
 #pragma unroll
