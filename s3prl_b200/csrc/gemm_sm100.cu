@@ -376,7 +376,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
                     const int kr = kb - kq * p.kb_per_row;
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     uint8_t* st = smem + stage * k2StageBytes;
-                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * k2StageBytes);
+                    // bytes of both CTAs: 2 x (A_hi + A_lo + two half-B planes of umma_n/2 rows)
+                    if (leader)
+                        mbar_arrive_expect_tx(&full_bar[stage],
+                                              2u * (2u * k2TileBytes + 2u * (uint32_t)(p.umma_n >> 1) * k2BlockK * 2u));
                     else mbar_arrive_remote(&full_bar[stage], 0);
                     const int a_row = row0 + kq * p.a_row_step + p.a_row_off;
                     tma_load_3d_2cta(st, &p.a_hi, &full_bar[stage], a_k0 + kr * k2BlockK, a_row, batch);
@@ -449,7 +452,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
             __syncwarp();
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * kAccCols;
-            for (int c = chalf * 128; c < chalf * 128 + 128; c += 32) {
+            const int chw = p.umma_n >> 1;  // columns per epilogue warp group (128 or 64)
+            for (int c = chalf * chw; c < (chalf + 1) * chw; c += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32(t_row + (uint32_t)c, v);
                 tmem_ld_wait();
@@ -481,7 +485,8 @@ static cudaError_t launch_pair(const GemmParams& p, int sm_count, cudaStream_t s
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    if (p.umma_n != 256 || p.block_k != k2BlockK || !p.b_n_tiled || p.b_z_per_ntile != 0) return cudaErrorInvalidValue;
+    if ((p.umma_n != 256 && p.umma_n != 128) || p.block_k != k2BlockK || !p.b_n_tiled || p.b_z_per_ntile != 0)
+        return cudaErrorInvalidValue;
     const int num_pt = p.batches * ((p.tiles_m_per_batch + 1) / 2) * p.n_tiles;
     if (num_pt <= 0) return cudaSuccess;
     const int clusters = num_pt < sm_count / 2 ? num_pt : sm_count / 2;

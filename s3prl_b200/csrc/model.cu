@@ -31,6 +31,7 @@ using namespace s3b;
 // errors
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_last_error;
+static int g_sm_count = 148;  // SM count of the device in use (refreshed by s3b_model_finalize)
 
 static int fail(const char* fmt, ...) {
     char buf[1024];
@@ -293,6 +294,7 @@ extern "C" int s3b_model_finalize(s3b_model* m) {
     CUDA_OK(cudaGetDeviceProperties(&prop, dev));
     if (prop.major != 10) return fail("device is sm_%d%d; this library contains sm_100a code only", prop.major, prop.minor);
     m->sm_count = prop.multiProcessorCount;
+    g_sm_count = m->sm_count;
 
     const s3b_config& c = m->cfg;
     const int D = c.embed_dim, F = c.ffn_dim, C = kConvDim;
@@ -465,13 +467,32 @@ static void set_epi(GemmParams& p, const Epi& e, int ldo) {
 }
 
 // 256-column tiles run on CTA pairs (cta_group::2) unless S3B_GEMM_PAIR=0 (kept for A/B measurements)
-static int use_cta_pairs(int umma_n) {
+static int pairs_enabled() {
     static int enabled = -1;
     if (enabled < 0) {
         const char* e = getenv("S3B_GEMM_PAIR");
         enabled = (e == nullptr || e[0] != '0') ? 1 : 0;
     }
-    return (umma_n == 256 && enabled) ? 1 : 0;
+    return enabled;
+}
+static int use_cta_pairs(int umma_n) { return ((umma_n == 256 || umma_n == 128) && pairs_enabled()) ? 1 : 0; }
+
+// Tile width for a flat [M][N] linear layer on CTA pairs: 256 columns unless the (256 x 256)-tile count leaves most
+// of the 74 clusters idle or badly quantised (small per-GPU batches when the utterances are sharded over 8 GPUs);
+// cost ~ rounds x (columns + fixed per-tile overhead).
+static int pick_pair_umma_n(int64_t M, int N, int sm_count) {
+    if (N % 256 != 0) return (N % 128 == 0) ? 128 : 0;
+    const int clusters = sm_count / 2 > 0 ? sm_count / 2 : 1;
+    const int64_t pairs = ((M + 127) / 128 + 1) / 2;
+    int best = 256;
+    double best_cost = 1e30;
+    for (int un = 256; un >= 128; un -= 128) {
+        const int64_t tiles = pairs * (N / un);
+        const int64_t rounds = (tiles + clusters - 1) / clusters;
+        const double cost = (double)rounds * (un + 48);
+        if (cost < best_cost - 1e-9) best_cost = cost, best = un;
+    }
+    return best;
 }
 
 static int pick_umma_n(int N) {
@@ -495,7 +516,8 @@ static int linear_params(GemmParams& p, const __nv_bfloat16* a_hi, const __nv_bf
     memset(&p, 0, sizeof(p));
     if (K % 64 != 0 || N % 16 != 0)  // K % 64 keeps both k-block widths legal
         return fail("linear: K %% 64 or N %% 16 violated (N=%d K=%d)", N, K);
-    const int un = pick_umma_n(N);
+    int un = pick_umma_n(N);
+    if (pairs_enabled() && pick_pair_umma_n(M, N, g_sm_count) != 0) un = pick_pair_umma_n(M, N, g_sm_count);
     const int pair = use_cta_pairs(un);
     const int bk = pair ? 64 : gemm_block_k(un);
     const int bbox = pair ? un / 2 : un;  // CTA pairs: each CTA loads half of the tile's W rows
