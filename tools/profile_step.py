@@ -35,3 +35,19 @@ with torch.no_grad():
     e1.record()
     torch.cuda.synchronize()
 print(f"{args.model}: {e0.elapsed_time(e1) / args.steps:.3f} ms/step (not a bench number when run under ncu)")
+
+# optional per-category device-time breakdown (CUDA events around every launch)
+import ctypes as C  # noqa: E402
+
+from s3prl_b200 import lib as s3lib  # noqa: E402
+
+native = expert._native
+s3lib.check(native.lib.s3b_profile_enable(native.handle, 1))
+with torch.no_grad():
+    for _ in range(args.steps):
+        weighted_sum(expert(wavs)["hidden_states"], w)
+ms5, fl5, ln5 = (C.c_double * 5)(), (C.c_double * 5)(), (C.c_int64 * 5)()
+s3lib.check(native.lib.s3b_profile_read(native.handle, ms5, fl5, ln5, 1))
+names = ["gemm", "attention", "conv0", "layernorm", "misc"]
+print("breakdown ms/step:", {n: round(ms5[i] / args.steps, 3) for i, n in enumerate(names)},
+      "launches/step:", sum(ln5) // args.steps)
