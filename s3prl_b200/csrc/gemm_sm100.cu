@@ -58,9 +58,20 @@ __device__ __forceinline__ void store_split(__nv_bfloat16* dhi, __nv_bfloat16* d
 }
 
 // Epilogue for NC (16 or 32) consecutive accumulator columns of one output row.
+// residual row segment for NC columns, issued early so that its global-load latency overlaps the TMEM load and
+// the previous chunk's math (out_proj / fc2 epilogues were stalling on these loads, profiles/r1c)
+template <int NC>
+__device__ __forceinline__ void load_residual(const GemmParams& p, bool row_ok, size_t m, int col, float4 (&r)[NC / 4]) {
+    if (p.residual != nullptr && row_ok && !p.qkv_mode) {
+        const float4* r4 = reinterpret_cast<const float4*>(p.residual + m * (size_t)p.ldo + col);
+#pragma unroll
+        for (int j = 0; j < NC / 4; ++j) r[j] = __ldg(r4 + j);
+    }
+}
+
 template <int NC>
 __device__ __forceinline__ void epilogue_cols(const GemmParams& p, const uint32_t (&v)[NC], bool row_ok, size_t m,
-                                              int col, bool masked) {
+                                              int col, bool masked, const float4 (&res)[NC / 4]) {
     float x[NC];
 #pragma unroll
     for (int j = 0; j < NC; ++j) x[j] = __uint_as_float(v[j]);
@@ -111,10 +122,9 @@ __device__ __forceinline__ void epilogue_cols(const GemmParams& p, const uint32_
 
     const size_t off = m * (size_t)p.ldo + col;
     if (p.residual != nullptr) {
-        const float4* r4 = reinterpret_cast<const float4*>(p.residual + off);
 #pragma unroll
         for (int j = 0; j < NC / 4; ++j) {
-            const float4 r = r4[j];
+            const float4 r = res[j];
             x[4 * j] += r.x, x[4 * j + 1] += r.y, x[4 * j + 2] += r.z, x[4 * j + 3] += r.w;
         }
     }
@@ -267,15 +277,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16x3_kernel(const __grid_c
             int c = 0;
             for (; c + 32 <= p.umma_n; c += 32) {
                 uint32_t v[32];
+                float4 res[8];
+                load_residual<32>(p, row_ok, m, col0 + c, res);
                 tmem_ld_32x32(t_row + (uint32_t)c, v);
                 tmem_ld_wait();
-                epilogue_cols<32>(p, v, row_ok, m, col0 + c, masked);
+                epilogue_cols<32>(p, v, row_ok, m, col0 + c, masked, res);
             }
             if (c < p.umma_n) {  // 16-column tail (umma_n % 32 == 16)
                 uint32_t v[16];
+                float4 res[4];
+                load_residual<16>(p, row_ok, m, col0 + c, res);
                 tmem_ld_32x16(t_row + (uint32_t)c, v);
                 tmem_ld_wait();
-                epilogue_cols<16>(p, v, row_ok, m, col0 + c, masked);
+                epilogue_cols<16>(p, v, row_ok, m, col0 + c, masked, res);
             }
             tc_fence_before();
             __syncwarp();
@@ -453,11 +467,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * kAccCols;
             const int chw = p.umma_n >> 1;  // columns per epilogue warp group (128 or 64)
+            float4 res_next[8];
+            load_residual<32>(p, row_ok, m, col0 + chalf * chw, res_next);
             for (int c = chalf * chw; c < (chalf + 1) * chw; c += 32) {
                 uint32_t v[32];
+                float4 res[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) res[j] = res_next[j];
                 tmem_ld_32x32(t_row + (uint32_t)c, v);
+                if (c + 32 < (chalf + 1) * chw) load_residual<32>(p, row_ok, m, col0 + c + 32, res_next);
                 tmem_ld_wait();
-                epilogue_cols<32>(p, v, row_ok, m, col0 + c, masked);
+                epilogue_cols<32>(p, v, row_ok, m, col0 + c, masked, res);
             }
             tc_fence_before();
             __syncwarp();

@@ -52,41 +52,59 @@ cudaError_t launch_wavlm_rel_table(const float* emb, int num_buckets, int max_di
     return e;
 }
 
-// one warp per (token, head): 64 inputs -> 8 outputs -> 2 gates
+// one thread per (token, head): 64 inputs -> 8 outputs -> 2 gates; grep_linear (8 x 64 + 8) staged in smem
 __global__ void __launch_bounds__(256) wavlm_gate_kernel(const __nv_bfloat16* __restrict__ x_hi,
                                                          const __nv_bfloat16* __restrict__ x_lo, size_t M, int T,
                                                          int H, int D, const float* __restrict__ gw,
                                                          const float* __restrict__ gb, const float* __restrict__ ga,
                                                          float* __restrict__ gate) {
-    const size_t wid = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (wid >= M * (size_t)H) return;
-    const size_t m = wid / H;
-    const int h = (int)(wid - m * H);
+    __shared__ float sw[8 * 64 + 8];
+    if (gw != nullptr)
+        for (int i = threadIdx.x; i < 8 * 64 + 8; i += blockDim.x) sw[i] = i < 512 ? gw[i] : gb[i - 512];
+    __syncthreads();
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * (size_t)H) return;
+    const size_t m = idx / H;
+    const int h = (int)(idx - m * H);
     const int b = (int)(m / T), t = (int)(m - (size_t)b * T);
     float g1 = 1.0f;
     if (gw != nullptr) {
         const size_t off = m * (size_t)D + (size_t)h * 64;
-        const float x0 = __bfloat162float(x_hi[off + lane]) + __bfloat162float(x_lo[off + lane]);
-        const float x1 = __bfloat162float(x_hi[off + lane + 32]) + __bfloat162float(x_lo[off + lane + 32]);
+        const uint4* ph = reinterpret_cast<const uint4*>(x_hi + off);
+        const uint4* pl = reinterpret_cast<const uint4*>(x_lo + off);
         float u[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) u[j] = warp_sum(gw[j * 64 + lane] * x0 + gw[j * 64 + lane + 32] * x1) + gb[j];
+        for (int j = 0; j < 8; ++j) u[j] = sw[512 + j];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {  // 8 bf16 per 16-byte chunk
+            const uint4 vh = ph[c], vl = pl[c];
+            const uint32_t wh[4] = {vh.x, vh.y, vh.z, vh.w}, wl[4] = {vl.x, vl.y, vl.z, vl.w};
+            float xv[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                xv[2 * e] = __uint_as_float(wh[e] << 16) + __uint_as_float(wl[e] << 16);
+                xv[2 * e + 1] = __uint_as_float(wh[e] & 0xffff0000u) + __uint_as_float(wl[e] & 0xffff0000u);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) u[j] = fmaf(sw[j * 64 + c * 8 + e], xv[e], u[j]);
+        }
         const float sa = (u[0] + u[1]) + (u[2] + u[3]);
         const float sb = (u[4] + u[5]) + (u[6] + u[7]);
         const float a = 1.0f / (1.0f + expf(-sa));
         const float bb = 1.0f / (1.0f + expf(-sb));
         g1 = a * (bb * ga[h] - 1.0f) + 2.0f;
     }
-    if (lane == 0) gate[((size_t)b * H + h) * T + t] = g1;
+    gate[((size_t)b * H + h) * T + t] = g1;
 }
 
 cudaError_t launch_wavlm_gate(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, size_t M, int B, int T, int H,
                               int D, const float* grep_w, const float* grep_b, const float* grep_a, float* gate,
                               cudaStream_t s) {
     (void)B;
-    const size_t warps = M * (size_t)H;
-    const unsigned blocks = (unsigned)((warps + 7) / 8);
+    const size_t n = M * (size_t)H;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
     wavlm_gate_kernel<<<blocks, 256, 0, s>>>(x_hi, x_lo, M, T, H, D, grep_w, grep_b, grep_a, gate);
     return cudaGetLastError();
 }
