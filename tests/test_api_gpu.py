@@ -1,0 +1,58 @@
+"""GPU tests of the host-side API mirrors: Featurizer (forward + backward of the layer weights) and S3PRLUpstream."""
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT / "oracle"))
+pytestmark = pytest.mark.gpu
+
+
+def test_featurizer_forward_backward(s3b_lib):
+    import upstream_oracle as O
+    from s3prl_b200.hub import hubert_base
+    from s3prl_b200.upstream.featurizer import Featurizer
+
+    up = hubert_base().to("cuda")
+    feat = Featurizer(up, "hidden_states", upstream_device="cuda")
+    assert feat.layer_num == 13 and feat.output_dim == 768 and feat.downsample_rate == 320
+    g = torch.Generator().manual_seed(3)
+    wavs = [torch.randn(n, generator=g).cuda() for n in (16000, 12000, 6400)]
+    with torch.no_grad():
+        res = up(wavs)
+    with torch.no_grad():
+        feat.weights.copy_(torch.randn(13, generator=g).cuda())
+    out = feat(wavs, res)
+    assert [o.shape[0] for o in out] == O.featurizer_lengths([16000, 12000, 6400])
+    ref_full = O.weighted_sum([h.cpu() for h in res["hidden_states"]], feat.weights.detach().cpu())
+    for o, n, r in zip(out, [50, 38, 20], ref_full):
+        assert torch.allclose(o.detach().cpu(), r[:n], atol=1e-5, rtol=1e-5)
+    # gradient of the 13 layer weights vs autograd through the plain torch formulation
+    loss = sum((o * o).sum() for o in out)
+    loss.backward()
+    w = feat.weights.detach().clone().requires_grad_(True)
+    stacked = torch.stack([h.detach() for h in res["hidden_states"]], 0)
+    ws = (torch.softmax(w, -1).view(-1, 1, 1, 1) * stacked).sum(0)
+    ref_loss = sum((ws[i, :n] ** 2).sum() for i, n in enumerate([50, 38, 20]))
+    ref_loss.backward()
+    assert torch.allclose(feat.weights.grad, w.grad, rtol=2e-3, atol=1e-3 * w.grad.abs().max().item())
+
+
+def test_s3prl_upstream_wrapper(s3b_lib):
+    import upstream_oracle as O
+    from s3prl_b200.nn import S3PRLUpstream
+
+    model = S3PRLUpstream("hubert_base").to("cuda")
+    assert model.num_layers == 13 and model.hidden_sizes == [768] * 13 and model.downsample_rates == [320] * 13
+    lens = torch.tensor([16000, 9000, 3200])
+    wavs = torch.zeros(3, 16000)
+    g = torch.Generator().manual_seed(4)
+    for i, n in enumerate(lens.tolist()):
+        wavs[i, :n] = torch.randn(n, generator=g)
+    all_hs, all_lens = model(wavs.cuda(), lens.cuda())
+    assert len(all_hs) == 13
+    assert all_lens[0].tolist() == O.s3prl_upstream_lengths(lens.tolist())
+    assert all_hs[0].shape == (3, 50, 768)  # len(range(0, 16000, 320)) == 50: last frame repeated once
+    assert torch.equal(all_hs[3][:, 49], all_hs[3][:, 48])
