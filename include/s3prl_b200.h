@@ -108,6 +108,17 @@ int s3b_weighted_sum_backward(const float* hs, int32_t num, int64_t n_per_layer,
 int64_t s3b_fbank_num_frames(int64_t len);
 int s3b_fbank(const float* const* wavs, const int64_t* lens, int32_t batch, float* out, void* stream);
 
+/* mel / linear baseline upstreams (s3prl/upstream/baseline/expert.py:52-79 over OnlinePreprocessor.forward,
+ * s3prl/upstream/baseline/preprocessor.py:150-223; mel.yaml / linear.yaml). The host side (Python, like the
+ * reference) derives the data-dependent lengths; these entry points do the arithmetic.
+ *  s3b_trimmed_lengths: out[b] = (index of the last non-zero sample) + 1, or lens[b] if all zero (synchronous).
+ *  s3b_melspec: STFT power (n_fft 400, hop 160, hann, center/reflect over the row padded to `padded_len`) ->
+ *    mel != 0: 80-bin HTK mel, else 201 linear bins -> log(x + 1e-10) -> CMVN over the first feats_len[b] frames
+ *    -> first final_len[b] frames kept, zero up to t_out. out: DEVICE [batch][t_out][80 | 201] fp32. */
+int s3b_trimmed_lengths(const float* const* wavs, const int64_t* lens, int32_t batch, int64_t* out);
+int s3b_melspec(const float* const* wavs, const int64_t* trimmed_lens, int32_t batch, int64_t padded_len, int32_t mel,
+                const int32_t* feats_len, const int32_t* final_len, int32_t t_out, float* out, void* stream);
+
 /* Building blocks exposed for parity tests (device pointers, fp32) -------------------------------------- */
 /* out[M][N] = act(A[M][K] * W[N][K]^T + bias[N]) (+ residual[M][N]); K % 64 == 0, N % 16 == 0 */
 int s3b_linear_f32(const float* a, const float* w, const float* bias, const float* residual, int64_t m, int32_t n,

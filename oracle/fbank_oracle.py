@@ -73,3 +73,46 @@ def fbank_forward(wavs: Sequence[torch.Tensor]) -> torch.Tensor:
         f = (f - f.mean(dim=0, keepdim=True)) / (1e-10 + f.std(dim=0, keepdim=True))
         feats.append(f)
     return torch.nn.utils.rnn.pad_sequence(feats, batch_first=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# mel / linear (torch.stft path): s3prl/upstream/baseline/preprocessor.py:150-223 + expert.py:52-79
+# ------------------------------------------------------------------------------------------------
+def melscale_fbanks_htk(n_freqs: int = 201, n_mels: int = 80, f_max: float = 8000.0, sample_rate: int = 16000) -> torch.Tensor:
+    """torchaudio.functional.melscale_fbanks(201, 0, 8000, 80, 16000, norm=None, mel_scale="htk") -> [201, 80]."""
+    all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    m_min, m_max = 0.0, 2595.0 * math.log10(1.0 + f_max / 700.0)
+    m_pts = torch.linspace(m_min, m_max, n_mels + 2)
+    f_pts = 700.0 * (10.0 ** (m_pts / 2595.0) - 1.0)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    down = -slopes[:, :-2] / f_diff[:-1]
+    up = slopes[:, 2:] / f_diff[1:]
+    return torch.max(torch.zeros(1), torch.min(down, up))
+
+
+def spectrogram_forward(wavs: Sequence[torch.Tensor], feat_type: str = "mel") -> torch.Tensor:
+    """[B, T_out, 80 | 201] for the `mel` / `linear` upstreams, length quirks of the reference included."""
+    eps = 1e-10
+    orig_lens = [len(w) for w in wavs]
+    trimmed = []
+    for w in wavs:  # last non-zero sample + 1 (the whole thing if all zero), preprocessor.py:166-175
+        nz = w.nonzero()
+        trimmed.append(len(w) if len(nz) == 0 else int(nz[:, -1].max()) + 1)
+    x = torch.nn.utils.rnn.pad_sequence([w[:n].float() for w, n in zip(wavs, trimmed)], batch_first=True)
+    spec = torch.stft(x, n_fft=400, hop_length=160, win_length=400, window=torch.hann_window(400), center=True,
+                      pad_mode="reflect", normalized=False, onesided=True, return_complex=True)
+    feat = spec.abs().pow(2)  # [B, 201, n_frames]
+    if feat_type == "mel":
+        feat = (feat.transpose(-1, -2) @ melscale_fbanks_htk()).transpose(-1, -2)
+    feat = (feat + eps).log()
+    downsample_rate = x.size(-1) / feat.size(-1)
+    feats_len = [round(n / downsample_rate) for n in trimmed]
+    outs = []
+    for f, n in zip(feat, feats_len):
+        f = f[:, :n]
+        outs.append(((f - f.mean(dim=-1, keepdim=True)) / (f.std(dim=-1, keepdim=True) + eps)).transpose(-1, -2))
+    feats = torch.nn.utils.rnn.pad_sequence(outs, batch_first=True)
+    ratio = len(feats[0]) / orig_lens[0]  # expert.py:62 uses the FIRST utterance's length
+    final = [round(n * ratio) for n in orig_lens]
+    return torch.nn.utils.rnn.pad_sequence([f[:n] for f, n in zip(feats, final)], batch_first=True)

@@ -214,6 +214,26 @@ def make_fbank_fixture():
     torch.save(out, GOLDEN / "fbank.pt")
 
 
+def make_spectrogram_fixture():
+    """s3prl.upstream.baseline mel / linear entries (torch.stft path) on equal-length and ragged batches."""
+    from s3prl.upstream.baseline.hubconf import linear, mel
+
+    out = {"cases": []}
+    for name, factory in (("mel", mel), ("linear", linear)):
+        expert = factory()
+        expert.eval()
+        torch.manual_seed(0)
+        c1 = [torch.randn(16000) for _ in range(4)]
+        ragged = seeded_wavs([16000, 9999, 4000, 1234], 654)
+        ragged[1][-37:] = 0.0  # trailing exact zeros exercise the non-zero trimming rule
+        for cname, wavs in (("4x1s_seed0", c1), ("ragged", ragged)):
+            with torch.no_grad():
+                hs = expert(wavs)["hidden_states"][0]
+            out["cases"].append({"feat": name, "name": cname, "lens": [len(w) for w in wavs], "out": hs.float().clone()})
+            print(f"{name} {cname}: {tuple(hs.shape)}")
+    torch.save(out, GOLDEN / "spectrogram.pt")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -224,6 +244,8 @@ def main():
         make_integer_fixture()
     if args.only in (None, "fbank"):
         make_fbank_fixture()
+    if args.only in (None, "spectrogram"):
+        make_spectrogram_fixture()
     for name in CASES:
         if args.only in (None, name):
             make_model_fixture(name)

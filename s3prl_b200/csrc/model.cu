@@ -1071,3 +1071,49 @@ extern "C" int s3b_fbank(const float* const* wavs, const int64_t* lens, int32_t 
     CUDA_OK(launch_fbank(d_ptrs, d_lens, batch, (int)max_frames, out, st));
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// mel / linear baselines (s3prl/upstream/baseline/expert.py:52-79 over preprocessor.py:150-223)
+// ------------------------------------------------------------------------------------------------
+extern "C" int s3b_trimmed_lengths(const float* const* wavs, const int64_t* lens, int32_t batch, int64_t* out) {
+    if (!wavs || !lens || !out) return fail("null argument");
+    if (s3b_device_count() == 0) return fail("no CUDA device: s3prl_b200 has no CPU fallback");
+    DevBuf scratch;
+    S3B_OK(scratch.ensure((size_t)batch * (sizeof(void*) + 2 * sizeof(long long))));
+    const float** d_ptrs = scratch.as<const float*>();
+    long long* d_lens = reinterpret_cast<long long*>(scratch.as<char>() + (size_t)batch * sizeof(void*));
+    long long* d_out = d_lens + batch;
+    std::vector<long long> l64(lens, lens + batch), res(batch);
+    CUDA_OK(cudaMemcpy(d_ptrs, wavs, batch * sizeof(void*), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(d_lens, l64.data(), batch * sizeof(long long), cudaMemcpyHostToDevice));
+    CUDA_OK(launch_trimmed_lengths(d_ptrs, d_lens, batch, d_out, 0));
+    CUDA_OK(cudaMemcpy(res.data(), d_out, batch * sizeof(long long), cudaMemcpyDeviceToHost));
+    for (int b = 0; b < batch; ++b) out[b] = res[b];
+    scratch.release();
+    return 0;
+}
+
+extern "C" int s3b_melspec(const float* const* wavs, const int64_t* trimmed_lens, int32_t batch, int64_t padded_len,
+                           int32_t mel, const int32_t* feats_len, const int32_t* final_len, int32_t t_out, float* out,
+                           void* stream) {
+    if (!wavs || !trimmed_lens || !feats_len || !final_len || !out) return fail("null argument");
+    if (batch < 1 || padded_len < 1 || t_out < 1) return fail("bad sizes");
+    if (s3b_device_count() == 0) return fail("no CUDA device: s3prl_b200 has no CPU fallback");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int dim = mel ? 80 : 201;
+    const int64_t n_frames = 1 + padded_len / 160;
+    static thread_local DevBuf scratch, tmp;
+    S3B_OK(scratch.ensure((size_t)batch * (sizeof(void*) + sizeof(long long) + 2 * sizeof(int))));
+    S3B_OK(tmp.ensure((size_t)batch * n_frames * dim * 4));
+    const float** d_ptrs = scratch.as<const float*>();
+    long long* d_lens = reinterpret_cast<long long*>(scratch.as<char>() + (size_t)batch * sizeof(void*));
+    int* d_fl = reinterpret_cast<int*>(d_lens + batch);
+    int* d_kl = d_fl + batch;
+    std::vector<long long> l64(trimmed_lens, trimmed_lens + batch);
+    CUDA_OK(cudaMemcpyAsync(d_ptrs, wavs, batch * sizeof(void*), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(d_lens, l64.data(), batch * sizeof(long long), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(d_fl, feats_len, batch * sizeof(int), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(d_kl, final_len, batch * sizeof(int), cudaMemcpyHostToDevice, st));
+    CUDA_OK(launch_melspec(d_ptrs, d_lens, batch, padded_len, mel, d_fl, d_kl, t_out, tmp.as<float>(), out, st));
+    return 0;
+}

@@ -56,6 +56,24 @@ def fbank(*args, **kwargs):
 ENTRIES["fbank"] = fbank
 
 
+def mel(*args, **kwargs):
+    """80-bin log-mel spectrogram + CMVN (s3prl/upstream/baseline/hubconf.py mel entry, mel.yaml)."""
+    from .upstream.baseline import SpectrogramExpert
+
+    return SpectrogramExpert("mel")
+
+
+def linear(*args, **kwargs):
+    """201-bin log power spectrogram + CMVN (s3prl/upstream/baseline/hubconf.py linear entry, linear.yaml)."""
+    from .upstream.baseline import SpectrogramExpert
+
+    return SpectrogramExpert("linear")
+
+
+ENTRIES["mel"] = mel
+ENTRIES["linear"] = linear
+
+
 def options() -> List[str]:
     """Names of the available entries (cf. s3prl.hub.options, s3prl/hub.py:40-54)."""
     return sorted(ENTRIES)

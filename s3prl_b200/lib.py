@@ -34,6 +34,8 @@ EXPORTED_SYMBOLS = [
     "s3b_attention_f32",
     "s3b_fbank",
     "s3b_fbank_num_frames",
+    "s3b_trimmed_lengths",
+    "s3b_melspec",
 ]
 
 
@@ -110,6 +112,8 @@ def load() -> C.CDLL:
     lib.s3b_fbank_num_frames.argtypes = [i64]
     lib.s3b_fbank_num_frames.restype = i64
     lib.s3b_fbank.argtypes = [C.POINTER(vp), C.POINTER(i64), i32, f32p, vp]
+    lib.s3b_trimmed_lengths.argtypes = [C.POINTER(vp), C.POINTER(i64), i32, C.POINTER(i64)]
+    lib.s3b_melspec.argtypes = [C.POINTER(vp), C.POINTER(i64), i32, i64, i32, C.POINTER(i32), C.POINTER(i32), i32, f32p, vp]
     _lib = lib
     return lib
 
