@@ -25,9 +25,10 @@ def test_featurizer_forward_backward(s3b_lib):
     with torch.no_grad():
         feat.weights.copy_(torch.randn(13, generator=g).cuda())
     out = feat(wavs, res)
-    assert [o.shape[0] for o in out] == O.featurizer_lengths([16000, 12000, 6400])
+    T = res["hidden_states"][0].shape[1]  # 49: slicing f[:round(len/320)] clamps at the frame count, as in the reference
+    assert [o.shape[0] for o in out] == [min(n, T) for n in O.featurizer_lengths([16000, 12000, 6400])]
     ref_full = O.weighted_sum([h.cpu() for h in res["hidden_states"]], feat.weights.detach().cpu())
-    for o, n, r in zip(out, [50, 38, 20], ref_full):
+    for o, n, r in zip(out, [49, 38, 20], ref_full):
         assert torch.allclose(o.detach().cpu(), r[:n], atol=1e-5, rtol=1e-5)
     # gradient of the 13 layer weights vs autograd through the plain torch formulation
     loss = sum((o * o).sum() for o in out)
@@ -35,7 +36,7 @@ def test_featurizer_forward_backward(s3b_lib):
     w = feat.weights.detach().clone().requires_grad_(True)
     stacked = torch.stack([h.detach() for h in res["hidden_states"]], 0)
     ws = (torch.softmax(w, -1).view(-1, 1, 1, 1) * stacked).sum(0)
-    ref_loss = sum((ws[i, :n] ** 2).sum() for i, n in enumerate([50, 38, 20]))
+    ref_loss = sum((ws[i, :n] ** 2).sum() for i, n in enumerate([49, 38, 20]))
     ref_loss.backward()
     assert torch.allclose(feat.weights.grad, w.grad, rtol=2e-3, atol=1e-3 * w.grad.abs().max().item())
 
