@@ -53,6 +53,18 @@ def algorithmic_flops_per_utt(cfg, L):
     return conv + proj + pos + lin + attn, T
 
 
+def gemm_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch (average over the launches of one step) from the
+    committed ncu capture of `tools/profile_step.py` (profiles/r1_traffic.json, see profiles/README.md); None if absent."""
+    try:
+        t = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text())
+        fam = [v for k, v in t.items() if k.startswith("gemm")]
+        n = sum(v["launches"] for v in fam)
+        return sum(v["dram_bytes_per_launch"] * v["launches"] for v in fam) / n if n else None
+    except Exception:
+        return None
+
+
 def seeded_wav(idx: int, n: int):
     import torch
 
@@ -327,8 +339,9 @@ def run_ours(args):
         "roofline": {
             "kernel": "gemm_bf16x3_kernel (tcgen05, all GEMM launches of a step)", "bound": "tensor",
             "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tflops / peak_tf,
-            "traffic": None, "peak_source": peak_src,
-            "note": "achieved = algorithmic FLOPs (1 MMA per product; the 3x split MMAs are not counted) / CUDA-event time per launch, rank 0",
+            "traffic": gemm_traffic(), "peak_source": peak_src,
+            "mma_pipe_tflops": 3.0 * gemm_tflops,
+            "note": "achieved = algorithmic FLOPs (1 MMA per product; the tensor pipe executes 3 bf16 MMAs per product = mma_pipe_tflops) / CUDA-event time per launch, rank 0; traffic = bytes per launch (ncu, profiles/)",
         },
         "kernel_breakdown": breakdown,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world},

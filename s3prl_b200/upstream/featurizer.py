@@ -55,6 +55,7 @@ class _WeightedSum(torch.autograd.Function):
                 )
             )
         ctx.save_for_backward(stacked, w)
+        ctx.weights_device = norm_weights.device
         return out
 
     @staticmethod
@@ -75,6 +76,7 @@ class _WeightedSum(torch.autograd.Function):
                         C.c_void_p(torch.cuda.current_stream(stacked.device).cuda_stream),
                     )
                 )
+            grad_w = grad_w.to(ctx.weights_device)  # the Featurizer's weights may live on another device
         if ctx.needs_input_grad[0]:
             grad_stacked = w.view(-1, *([1] * g.dim())) * g.unsqueeze(0)
         return grad_stacked, grad_w
