@@ -16,7 +16,7 @@ def test_featurizer_forward_backward(s3b_lib):
     from s3prl_b200.upstream.featurizer import Featurizer
 
     up = hubert_base().to("cuda")
-    feat = Featurizer(up, "hidden_states", upstream_device="cuda")
+    feat = Featurizer(up, "hidden_states", upstream_device="cuda").to("cuda")  # as Runner does (runner.py:166-180)
     assert feat.layer_num == 13 and feat.output_dim == 768 and feat.downsample_rate == 320
     g = torch.Generator().manual_seed(3)
     wavs = [torch.randn(n, generator=g).cuda() for n in (16000, 12000, 6400)]
