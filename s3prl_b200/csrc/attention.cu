@@ -62,8 +62,6 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
     const int q0 = (blockIdx.x - bh * q_tiles) * kQTile;
     const int b = bh / p.H;
     const int h = bh - b * p.H;
-    const int kv_len = p.kv_len[b];
-    const int nblk = (kv_len + kKBlk - 1) / kKBlk;
 
     if (tid == 0) {
         mbar_init(bar_q, 1);
@@ -94,6 +92,10 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_o = tmem_base + kColO;
+    pdl_wait();  // prologue overlapped the QKV GEMM's tail; global memory is touched only below
+    pdl_launch_dependents();
+    const int kv_len = p.kv_len[b];
+    const int nblk = (kv_len + kKBlk - 1) / kKBlk;
     const bool tracing = p.trace != nullptr && (int)blockIdx.x == p.trace_block;
 #define S3B_TR(role, j, slot)                                                         \
     do {                                                                              \
@@ -308,7 +310,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
 }
 
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t s) {
-    static bool attr_set = false;
+    static PerDeviceOnce attr_once;
+    bool& attr_set = attr_once.current();
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              kAttnSmem);
@@ -320,9 +323,9 @@ cudaError_t launch_attention(const AttnParams& p, cudaStream_t s) {
     const int q_tiles = (p.T + kQTile - 1) / kQTile;
     const int grid = p.B * p.H * q_tiles;
     if (grid <= 0) return cudaSuccess;
-    if (p.bias_table != nullptr) attention_kernel<true><<<grid, kAttnThreads, kAttnSmem, s>>>(p);
-    else attention_kernel<false><<<grid, kAttnThreads, kAttnSmem, s>>>(p);
-    return cudaGetLastError();
+    if (p.bias_table != nullptr)
+        return launch_pdl(attention_kernel<true>, dim3(grid), dim3(kAttnThreads), kAttnSmem, s, p);
+    return launch_pdl(attention_kernel<false>, dim3(grid), dim3(kAttnThreads), kAttnSmem, s, p);
 }
 
 }  // namespace s3b

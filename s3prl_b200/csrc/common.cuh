@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace s3b {
 
@@ -328,3 +329,47 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
 }
 
 }  // namespace s3b
+
+// Programmatic dependent launch (PDL): a kernel launched with the stream-serialization attribute may start its
+// prologue (barrier init, TMEM allocation, tensor-map prefetch) while the previous kernel of the stream drains;
+// `pdl_wait()` blocks until that previous grid has completed and its writes are visible, so every global read or
+// write of a kernel must come after it. `pdl_launch_dependents()` lets the next kernel's CTAs be scheduled as
+// soon as every CTA of this grid has issued it. Both are no-ops for a normal launch. S3B_PDL=0 disables.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("S3B_PDL");
+        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// cudaFuncSetAttribute applies to the current device only: one "done" flag per device so that a process that
+// drives several GPUs configures each of them.
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool& current() {
+        int d = 0;
+        cudaGetDevice(&d);
+        return done[d & 63];
+    }
+};

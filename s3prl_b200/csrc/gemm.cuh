@@ -56,6 +56,9 @@ struct GemmParams {
     __nv_bfloat16 *q_hi, *q_lo, *k_hi, *k_lo, *vt_hi, *vt_lo;
 
     double alg_flops;  // host-side accounting only: 2*M*N*K with the un-padded K
+
+    // debug timeline (tools/gemm_trace.py): 16 clock64 stamps of CTA 0, or nullptr
+    unsigned long long* trace;
 };
 
 // k-block width the kernel instantiation for this tile width uses (tensor-map boxes must match)

@@ -140,6 +140,109 @@ __device__ __forceinline__ void epilogue_cols(const GemmParams& p, const uint32_
     if (p.out_hi != nullptr) store_split<NC>(p.out_hi + off, p.out_lo + off, x);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Coalesced epilogue of one 32-row x 32-column accumulator chunk (CTA-pair kernel).
+// tcgen05.ld hands every thread one ROW (32 consecutive columns): storing that directly makes each warp store
+// touch 32 different 128-byte lines (16 B each), and the LSU then needs ~20-29 k cycles per 128 x 256 tile —
+// longer than the 12 k-blocks of MMAs of a K=768 GEMM (timeline in profiles/r1e_gemm_trace.txt). The chunk is
+// therefore transposed through a per-warp 4 KB shared-memory buffer (XOR-swizzled, conflict-free both ways):
+// afterwards lane l owns columns 4*(l&7)..+3 of rows it*4 + (l>>3), it = 0..7, so each warp-level residual load /
+// fp32 store covers 4 rows x 128 contiguous bytes (bf16 planes: 4 rows x 64 B).
+// ------------------------------------------------------------------------------------------------
+struct EpiRows {           // per-tile row bookkeeping of one lane in the transposed layout
+    size_t off[8];         // element offset of the output row start (normal: m*ldo, QKV q/k: (b*H*T + t)*64)
+    uint32_t ok_bits;      // bit it: row exists
+    uint32_t mask_bits;    // bit it: row is a padded frame (zeroed)
+};
+
+__device__ __forceinline__ void epi_rows_init(const GemmParams& p, EpiRows& er, int batch, int row_base, int lane,
+                                              bool masked_thread_row) {
+    er.ok_bits = 0, er.mask_bits = 0;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int src = it * 4 + (lane >> 3);
+        const int row = row_base + src;
+        const bool ok = row < p.rows_per_batch;
+        const size_t m = (size_t)batch * p.out_rows_per_batch + (ok ? row : 0);
+        if (p.qkv_mode) {
+            const int b = (int)(m / (size_t)p.T);
+            const int t = (int)(m - (size_t)b * p.T);
+            er.off[it] = ((size_t)b * p.H * p.T + t) * 64;
+        } else {
+            er.off[it] = m * (size_t)p.ldo;
+        }
+        er.ok_bits |= (ok ? 1u : 0u) << it;
+        er.mask_bits |= (__shfl_sync(0xffffffffu, masked_thread_row ? 1 : 0, src) ? 1u : 0u) << it;
+    }
+}
+
+__device__ __forceinline__ void epi_load_residual(const GemmParams& p, const EpiRows& er, int col, int lane,
+                                                  float4 (&r)[8]) {
+    if (p.residual != nullptr && !p.qkv_mode) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it)
+            if ((er.ok_bits >> it) & 1u)
+                r[it] = __ldg(reinterpret_cast<const float4*>(p.residual + er.off[it] + col) + (lane & 7));
+    }
+}
+
+// v: this thread's row (32 columns starting at `col`); stage: this warp's 4 KB buffer
+__device__ __forceinline__ void epi_chunk_coalesced(const GemmParams& p, const EpiRows& er, const uint32_t (&v)[32],
+                                                    uint8_t* stage, int col, int lane, const float4 (&res)[8],
+                                                    const float4& bias) {
+    const uint32_t sbase = smem_u32(stage);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t a = sbase + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[4 * j]), "r"(v[4 * j + 1]),
+                     "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                     : "memory");
+    }
+    __syncwarp();
+    const int cs = lane & 7;
+    // QKV scatter: 32-column chunks never straddle q/k/v or a head
+    int which = 0;
+    size_t head_off = 0;
+    if (p.qkv_mode) {
+        which = col / p.D;
+        const int within = col - which * p.D;
+        head_off = (size_t)(within >> 6) * p.T * 64 + (within & 63);
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3);
+        const uint32_t a = sbase + (uint32_t)r * 128u + (uint32_t)((cs ^ (r & 7)) << 4);
+        float4 x;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(a));
+        x.x += bias.x, x.y += bias.y, x.z += bias.z, x.w += bias.w;
+        if (p.gelu) x.x = gelu_erf(x.x), x.y = gelu_erf(x.y), x.z = gelu_erf(x.z), x.w = gelu_erf(x.w);
+        if (!((er.ok_bits >> it) & 1u)) continue;
+        if (p.qkv_mode) {
+            if (which == 0) x.x *= p.q_scale, x.y *= p.q_scale, x.z *= p.q_scale, x.w *= p.q_scale;
+            uint32_t h0, l0, h1, l1;
+            split_pack2(x.x, x.y, h0, l0);
+            split_pack2(x.z, x.w, h1, l1);
+            const size_t o = er.off[it] + head_off + 4 * cs;
+            *reinterpret_cast<uint2*>((which == 0 ? p.q_hi : p.k_hi) + o) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>((which == 0 ? p.q_lo : p.k_lo) + o) = make_uint2(l0, l1);
+            continue;
+        }
+        if (p.residual != nullptr) x.x += res[it].x, x.y += res[it].y, x.z += res[it].z, x.w += res[it].w;
+        if ((er.mask_bits >> it) & 1u) x = make_float4(0.f, 0.f, 0.f, 0.f);
+        const size_t o = er.off[it] + col + 4 * cs;
+        if (p.out_f32 != nullptr) *reinterpret_cast<float4*>(p.out_f32 + o) = x;
+        if (p.out_hi != nullptr) {
+            uint32_t h0, l0, h1, l1;
+            split_pack2(x.x, x.y, h0, l0);
+            split_pack2(x.z, x.w, h1, l1);
+            *reinterpret_cast<uint2*>(p.out_hi + o) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(p.out_lo + o) = make_uint2(l0, l1);
+        }
+    }
+    __syncwarp();  // the staging buffer is rewritten by the next chunk
+}
+
 template <int BLOCK_N, int BLOCK_K>
 __global__ void __launch_bounds__(kThreads, 1) gemm_bf16x3_kernel(const __grid_constant__ GemmParams p) {
     using Cfg = GemmCfg<BLOCK_N, BLOCK_K>;
@@ -183,6 +286,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16x3_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
+    pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
+    pdl_launch_dependents();
 
     const int tiles_m = p.batches * p.tiles_m_per_batch;
     const int num_tiles = tiles_m * p.n_tiles;
@@ -319,7 +424,9 @@ static constexpr int k2BlockK = 64;
 static constexpr int k2TileBytes = 128 * k2BlockK * 2;    // 16 KB: A plane (128 rows) or half-B plane (128 rows)
 static constexpr int k2StageBytes = 4 * k2TileBytes;      // A_hi A_lo B_hi B_lo
 static constexpr int k2Stages = 3;
-static constexpr int k2SmemBytes = k2Stages * k2StageBytes + 1024 + 256;
+static constexpr int k2EpiWarps = 8;
+static constexpr int k2EpiStageBytes = 32 * 32 * 4;  // per-warp transpose buffer of the coalesced epilogue
+static constexpr int k2SmemBytes = k2Stages * k2StageBytes + 256 + k2EpiWarps * k2EpiStageBytes + 1024;
 
 // 12 warps: TMA / MMA / TMEM-alloc / idle + EIGHT epilogue warps (two per TMEM lane quadrant, 128 columns each):
 // with four, the GELU + split epilogue of a K=768 tile (fc1, QKV) took longer than its 12 k-blocks of MMAs.
@@ -340,6 +447,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
+    const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+#define S3B_GTR(slot)                                        \
+    do {                                                     \
+        if (tracing) p.trace[slot] = (unsigned long long)clock64(); \
+    } while (0)
+    const long long t_entry = clock64();
 
     cluster_sync_all();  // both CTAs resident before the paired TMEM allocation
     if (warp == 0 && elect_one()) {
@@ -367,6 +480,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
+    const long long t_prologue = clock64();
+    pdl_wait();  // prologue overlapped the previous kernel's tail; global memory is touched only below
+    pdl_launch_dependents();
+    if (tracing && threadIdx.x == 0) {
+        p.trace[0] = (unsigned long long)t_entry;
+        p.trace[1] = (unsigned long long)t_prologue;
+        p.trace[2] = (unsigned long long)clock64();
+    }
 
     const int pairs_per_batch = (p.tiles_m_per_batch + 1) >> 1;
     const int num_pt = p.batches * pairs_per_batch * p.n_tiles;
@@ -421,6 +542,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
+                    if (done == 0 && kb == 0) S3B_GTR(3);
                     const uint32_t st = smem_u32(smem + stage * k2StageBytes);
                     const uint64_t da_hi = make_smem_desc<128>(st);
                     const uint64_t da_lo = make_smem_desc<128>(st + k2TileBytes);
@@ -437,6 +559,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
                     if (++stage == k2Stages) stage = 0, phase ^= 1u;
                 }
                 umma_commit_2cta(&tmem_full[acc]);
+                S3B_GTR(4);
                 if (++acc == 2) acc = 0, acc_phase ^= 1u;
             }
             // the peer's epilogue arrives remotely on this CTA's tmem_empty barriers: drain before teardown
@@ -449,9 +572,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
         // ===================== epilogue (both CTAs, 128 rows each) =====================
         const int ew = (warp - 4) & 3;        // TMEM lane quadrant (== warp % 4)
         const int chalf = (warp - 4) >> 2;    // which 128-column half of the accumulator this warp drains
+        uint8_t* epi_stage = smem + k2Stages * k2StageBytes + 256 + (warp - 4) * k2EpiStageBytes;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int pt = cluster_id; pt < num_pt; pt += num_clusters) {
+        const bool etr = tracing && warp == 4 && lane == 0;
+        int ntile_done = 0;
+        for (int pt = cluster_id; pt < num_pt; pt += num_clusters, ++ntile_done) {
             const int n_tile = pt % p.n_tiles;
             const int mp = pt / p.n_tiles;
             const int batch = mp / pairs_per_batch;
@@ -465,19 +591,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
             mbar_wait(&tmem_full[acc], acc_phase);
             __syncwarp();
             tc_fence_after();
+            if (etr) p.trace[ntile_done == 0 ? 5 : 7] = (unsigned long long)clock64();
             const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * kAccCols;
             const int chw = p.umma_n >> 1;  // columns per epilogue warp group (128 or 64)
+            EpiRows er;
+            epi_rows_init(p, er, batch, row0 + ew * 32, lane, masked);
             float4 res_next[8];
-            load_residual<32>(p, row_ok, m, col0 + chalf * chw, res_next);
+            epi_load_residual(p, er, col0 + chalf * chw, lane, res_next);
             for (int c = chalf * chw; c < (chalf + 1) * chw; c += 32) {
                 uint32_t v[32];
                 float4 res[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) res[j] = res_next[j];
                 tmem_ld_32x32(t_row + (uint32_t)c, v);
-                if (c + 32 < (chalf + 1) * chw) load_residual<32>(p, row_ok, m, col0 + c + 32, res_next);
+                if (c + 32 < (chalf + 1) * chw) epi_load_residual(p, er, col0 + c + 32, lane, res_next);
                 tmem_ld_wait();
-                epilogue_cols<32>(p, v, row_ok, m, col0 + c, masked, res);
+                if (p.qkv_mode && col0 + c >= 2 * p.D) {
+                    float4 none[8];
+                    epilogue_cols<32>(p, v, row_ok, m, col0 + c, masked, none);
+                } else {
+                    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.bias != nullptr) bias = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c) + (lane & 7));
+                    epi_chunk_coalesced(p, er, v, epi_stage, col0 + c, lane, res, bias);
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -485,8 +621,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
                 if (leader) mbar_arrive(&tmem_empty[acc]);
                 else mbar_arrive_remote(&tmem_empty[acc], 0);
             }
+            if (etr) p.trace[ntile_done == 0 ? 6 : 8] = (unsigned long long)clock64();
             if (++acc == 2) acc = 0, acc_phase ^= 1u;
         }
+        if (etr) p.trace[10] = (unsigned long long)ntile_done;
     }
 
     tc_fence_before();
@@ -495,10 +633,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
         tc_fence_after();
         tmem_dealloc_2cta(tmem_base, 2 * kAccCols);
     }
+    if (threadIdx.x == 0) S3B_GTR(9);
+#undef S3B_GTR
 }
 
 static cudaError_t launch_pair(const GemmParams& p, int sm_count, cudaStream_t stream) {
-    static bool attr_set = false;
+    static PerDeviceOnce attr_once;
+    bool& attr_set = attr_once.current();
     if (!attr_set) {
         cudaError_t e =
             cudaFuncSetAttribute(gemm2_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes);
@@ -510,14 +651,14 @@ static cudaError_t launch_pair(const GemmParams& p, int sm_count, cudaStream_t s
     const int num_pt = p.batches * ((p.tiles_m_per_batch + 1) / 2) * p.n_tiles;
     if (num_pt <= 0) return cudaSuccess;
     const int clusters = num_pt < sm_count / 2 ? num_pt : sm_count / 2;
-    gemm2_bf16x3_kernel<<<2 * clusters, k2Threads, k2SmemBytes, stream>>>(p);
-    return cudaGetLastError();
+    return launch_pdl(gemm2_bf16x3_kernel, dim3(2 * clusters), dim3(k2Threads), k2SmemBytes, stream, p);
 }
 
 template <int BLOCK_N, int BLOCK_K>
 static cudaError_t launch_impl(const GemmParams& p, int sm_count, cudaStream_t stream) {
     using Cfg = GemmCfg<BLOCK_N, BLOCK_K>;
-    static bool attr_set = false;
+    static PerDeviceOnce attr_once;
+    bool& attr_set = attr_once.current();
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gemm_bf16x3_kernel<BLOCK_N, BLOCK_K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::kSmemBytes);
@@ -527,8 +668,7 @@ static cudaError_t launch_impl(const GemmParams& p, int sm_count, cudaStream_t s
     const int num_tiles = p.batches * p.tiles_m_per_batch * p.n_tiles;
     if (num_tiles <= 0) return cudaSuccess;
     const int grid = num_tiles < sm_count ? num_tiles : sm_count;
-    gemm_bf16x3_kernel<BLOCK_N, BLOCK_K><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(p);
-    return cudaGetLastError();
+    return launch_pdl(gemm_bf16x3_kernel<BLOCK_N, BLOCK_K>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, p);
 }
 
 cudaError_t launch_gemm_bf16x3(const GemmParams& p, int sm_count, cudaStream_t stream) {

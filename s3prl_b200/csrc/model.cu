@@ -971,8 +971,33 @@ extern "C" int s3b_linear_f32(const float* a, const float* w, const float* bias,
         Epi e;
         e.bias = bias, e.residual = residual, e.gelu = gelu, e.out_f32 = out;
         set_epi(p, e, N);
+        // S3B_GEMM_TRACE=1: clock64 timeline of CTA 0 to stderr (tools/gemm_trace.py); 3 launches, last one traced
+        const bool trace = getenv("S3B_GEMM_TRACE") != nullptr;
+        unsigned long long* tr = nullptr;
+        if (trace && cudaMalloc(&tr, 16 * sizeof(unsigned long long)) == cudaSuccess) {
+            cudaMemsetAsync(tr, 0, 16 * sizeof(unsigned long long), st);
+            launch_gemm_bf16x3(p, sms, st);
+            launch_gemm_bf16x3(p, sms, st);
+            p.trace = tr;
+        }
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (trace) cudaEventCreate(&e0), cudaEventCreate(&e1), cudaEventRecord(e0, st);
         cudaError_t ce = launch_gemm_bf16x3(p, sms, st);
         if (ce != cudaSuccess) r = fail("gemm launch failed: %s", cudaGetErrorString(ce));
+        if (trace) {
+            cudaEventRecord(e1, st);
+            cudaStreamSynchronize(st);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            unsigned long long h[16] = {0};
+            if (tr) cudaMemcpy(h, tr, sizeof(h), cudaMemcpyDeviceToHost), cudaFree(tr);
+            fprintf(stderr, "gemm_trace M=%lld N=%d K=%d two_cta=%d umma_n=%d event_us=%.2f tiles_cta0=%llu :", (long long)M, N, K,
+                    p.two_cta, p.umma_n, ms * 1000.f, h[10]);
+            for (int i = 1; i < 14; ++i)
+                if (i != 10) fprintf(stderr, " t%d=%lld", i, h[i] ? (long long)(h[i] - h[0]) : -1LL);
+            fprintf(stderr, "\n");
+            cudaEventDestroy(e0), cudaEventDestroy(e1);
+        }
     }
     cudaError_t se = cudaStreamSynchronize(st);
     as.release(), ws.release();

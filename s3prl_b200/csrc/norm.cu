@@ -18,6 +18,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     constexpr int D = V4 * 128;
     const int lane = threadIdx.x & 31;
     const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    pdl_wait();
+    pdl_launch_dependents();
     if (row >= M) return;
     const float4* xr = reinterpret_cast<const float4*>(x + row * D);
     float4 v[V4];
@@ -62,14 +64,15 @@ cudaError_t launch_layernorm(const float* x, size_t M, int D, const float* gamma
                              float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t s) {
     if (M == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((M + 7) / 8);
+    cudaError_t e = cudaSuccess;
     switch (D) {
-        case 512: layernorm_kernel<4><<<blocks, 256, 0, s>>>(x, M, gamma, beta, gelu, out_f32, out_hi, out_lo); break;
-        case 768: layernorm_kernel<6><<<blocks, 256, 0, s>>>(x, M, gamma, beta, gelu, out_f32, out_hi, out_lo); break;
-        case 1024: layernorm_kernel<8><<<blocks, 256, 0, s>>>(x, M, gamma, beta, gelu, out_f32, out_hi, out_lo); break;
-        case 1280: layernorm_kernel<10><<<blocks, 256, 0, s>>>(x, M, gamma, beta, gelu, out_f32, out_hi, out_lo); break;
+        case 512: e = launch_pdl(layernorm_kernel<4>, dim3(blocks), dim3(256), 0, s, x, M, gamma, beta, gelu, out_f32, out_hi, out_lo); break;
+        case 768: e = launch_pdl(layernorm_kernel<6>, dim3(blocks), dim3(256), 0, s, x, M, gamma, beta, gelu, out_f32, out_hi, out_lo); break;
+        case 1024: e = launch_pdl(layernorm_kernel<8>, dim3(blocks), dim3(256), 0, s, x, M, gamma, beta, gelu, out_f32, out_hi, out_lo); break;
+        case 1280: e = launch_pdl(layernorm_kernel<10>, dim3(blocks), dim3(256), 0, s, x, M, gamma, beta, gelu, out_f32, out_hi, out_lo); break;
         default: return cudaErrorInvalidValue;
     }
-    return cudaGetLastError();
+    return e;
 }
 
 // ------------------------------------------------------------------------------------------------

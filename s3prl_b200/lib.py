@@ -10,7 +10,10 @@ import ctypes as C
 from pathlib import Path
 from typing import Optional
 
-_LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libs3prl_b200.so"
+import os
+
+# S3B_LIB_PATH: A/B runs of another build of the same C ABI on one box (tools/ab_step.sh); never a CPU fallback
+_LIB_PATH = Path(os.environ.get("S3B_LIB_PATH") or Path(__file__).resolve().parent / "_lib" / "libs3prl_b200.so")
 
 EXPORTED_SYMBOLS = [
     "s3b_version",
