@@ -87,3 +87,27 @@ def _check_model(name):
             # two fp32 CPU evaluations of the same math (different op order / BLAS blocking)
             assert rel < 2e-5, (name, l, rel)
             assert abs(h.double().norm().item() - case["norms"][l].item()) < 2e-5 * case["norms"][l].item()
+
+
+def test_gelu_formula():
+    """fp32 emulation of the device GELU (s3prl_b200/csrc/common.cuh gelu_erf: erfc by Abramowitz-Stegun 7.1.26)
+    against the float64 exact-erf GELU the reference computes in fp32 (nn.GELU(), wav2vec2_model.py:2893)."""
+    import math
+
+    import numpy as np
+
+    f = np.float32
+    x = np.concatenate([np.linspace(-12, 12, 400001), np.random.default_rng(0).standard_normal(200000) * 2]).astype(f)
+    z = (np.abs(x) * f(0.70710678118654752440)).astype(f)
+    t = (f(1) / (f(0.3275911) * z + f(1)).astype(f)).astype(f)
+    poly = f(1.061405429) * t + f(-1.453152027)
+    for c in (1.421413741, -0.284496736, 0.254829592):
+        poly = (poly * t + f(c)).astype(f)
+    e = np.exp2((z * (z * f(-1.4426950408889634))).astype(f)).astype(f)
+    erfc_z = (poly * t * e).astype(f)
+    out = (f(0.5) * x * np.where(x >= 0, f(2) - erfc_z, erfc_z)).astype(f)
+    xd = x.astype(np.float64)
+    ref = 0.5 * xd * (1 + np.vectorize(math.erf)(xd / math.sqrt(2)))
+    assert np.abs(out - ref).max() < 1e-6
+    torch_fp32 = torch.nn.functional.gelu(torch.from_numpy(x)).numpy()
+    assert np.abs(out - ref).max() <= np.abs(torch_fp32 - ref).max()  # at least as close to exact as torch's fp32 GELU
