@@ -505,7 +505,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
                 const int batch = mp / pairs_per_batch;
                 const int row0 = ((mp - batch * pairs_per_batch) * 2 + (int)rank) * kBlockM;
                 const int a_k0 = p.a_k_per_ntile * n_tile;
-                const int b_n0 = n_tile * p.umma_n + (int)rank * (p.umma_n >> 1);
+                const int b_n0 = (p.b_n_tiled ? n_tile * p.umma_n : 0) + (int)rank * (p.umma_n >> 1);
+                const int b_z0 = n_tile * p.b_z_per_ntile;
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     const int kq = kb / p.kb_per_row;
                     const int kr = kb - kq * p.kb_per_row;
@@ -520,8 +521,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
                     tma_load_3d_2cta(st, &p.a_hi, &full_bar[stage], a_k0 + kr * k2BlockK, a_row, batch);
                     tma_load_3d_2cta(st + k2TileBytes, &p.a_lo, &full_bar[stage], a_k0 + kr * k2BlockK, a_row, batch);
                     const int b_k = (p.b_k_linear ? kb : kr) * k2BlockK;
-                    tma_load_3d_2cta(st + 2 * k2TileBytes, &p.b_hi, &full_bar[stage], b_k, b_n0, 0);
-                    tma_load_3d_2cta(st + 3 * k2TileBytes, &p.b_lo, &full_bar[stage], b_k, b_n0, 0);
+                    const int b_z = p.b_k_linear ? 0 : b_z0 + kq;
+                    tma_load_3d_2cta(st + 2 * k2TileBytes, &p.b_hi, &full_bar[stage], b_k, b_n0, b_z);
+                    tma_load_3d_2cta(st + 3 * k2TileBytes, &p.b_lo, &full_bar[stage], b_k, b_n0, b_z);
                     if (++stage == k2Stages) stage = 0, phase ^= 1u;
                 }
             }
@@ -646,8 +648,8 @@ static cudaError_t launch_pair(const GemmParams& p, int sm_count, cudaStream_t s
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    if ((p.umma_n != 256 && p.umma_n != 128) || p.block_k != k2BlockK || !p.b_n_tiled || p.b_z_per_ntile != 0)
-        return cudaErrorInvalidValue;
+    // umma_n / 2 columns per epilogue warp group, in 32-column chunks
+    if ((p.umma_n != 256 && p.umma_n != 192 && p.umma_n != 128) || p.block_k != k2BlockK) return cudaErrorInvalidValue;
     const int num_pt = p.batches * ((p.tiles_m_per_batch + 1) / 2) * p.n_tiles;
     if (num_pt <= 0) return cudaSuccess;
     const int clusters = num_pt < sm_count / 2 ? num_pt : sm_count / 2;

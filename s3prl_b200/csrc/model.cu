@@ -153,7 +153,8 @@ struct s3b_model {
     SplitBuf conv_w[kNumConv];                             // 1..6, [512][kw*512] (tap-major K)
     DevBuf conv_b[kNumConv], conv_ln_g[kNumConv], conv_ln_b[kNumConv];
     DevBuf ln512_g, ln512_b, proj_b, pos_b, enc_ln_g, enc_ln_b;
-    SplitBuf proj_w, pos_w;
+    SplitBuf proj_w, pos_w, pos_w4;  // pos_w4: four-taps-per-k-block layout (posconv4_params)
+    DevBuf pos_z;                    // [B][T+3][4*D] fp32 scratch of the four-tap pos_conv GEMM
     DevBuf rel_table_src;  // WavLM relative_attention_bias.weight [num_buckets][H]
     std::vector<LayerW> layers;
 
@@ -266,13 +267,13 @@ extern "C" void s3b_model_destroy(s3b_model* m) {
                       &m->pos_b, &m->enc_ln_g, &m->enc_ln_b, &m->rel_table_src, &m->wav_ptrs, &m->lens_dev,
                       &m->kvlen_dev, &m->rowmask_dev, &m->wav_stats, &m->wav_pad, &m->c0_part, &m->c0_ss,
                       &m->conv_f32, &m->tmp_f32, &m->x_f32, &m->x1_f32, &m->gate, &m->rel_table, &m->stage_wav,
-                      &m->stage_out};
+                      &m->stage_out, &m->pos_z};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < kNumConv; ++i) {
         m->conv_w[i].release(), m->conv_b[i].release(), m->conv_ln_g[i].release(), m->conv_ln_b[i].release();
         m->act[i].release();
     }
-    SplitBuf* sb[] = {&m->proj_w, &m->pos_w, &m->ln512_s, &m->x_s, &m->xs_s, &m->q_s, &m->k_s, &m->vt_s, &m->ctx_s,
+    SplitBuf* sb[] = {&m->proj_w, &m->pos_w, &m->pos_w4, &m->ln512_s, &m->x_s, &m->xs_s, &m->q_s, &m->k_s, &m->vt_s, &m->ctx_s,
                       &m->x1_s, &m->h_s};
     for (SplitBuf* b : sb) b->release();
     for (LayerW& l : m->layers) {
@@ -359,6 +360,19 @@ extern "C" int s3b_model_finalize(s3b_model* m) {
                         wb[(((size_t)g * Kp + k) * cpg + n) * 64 + ci] = tv->data[((size_t)o * cpg + ci) * Kp + k] * scale[k];
                     }
         S3B_OK(upload_split(m->pos_w, wb.data(), wb.size()));
+        // four taps per k-block (tap = 4q + j): B operand [group*Kp/4 + q][n = j*cpg + co][64 (zero padded)]
+        if (Kp % 4 == 0) {
+            std::vector<float> w4((size_t)G * Kp * cpg * 64, 0.0f);
+            for (int g = 0; g < G; ++g)
+                for (int k = 0; k < Kp; ++k)
+                    for (int n = 0; n < cpg; ++n)
+                        for (int ci = 0; ci < cpg; ++ci) {
+                            const int q = k / 4, j = k % 4;
+                            w4[((((size_t)g * (Kp / 4) + q) * 4 + j) * cpg + n) * 64 + ci] =
+                                wb[(((size_t)g * Kp + k) * cpg + n) * 64 + ci];
+                        }
+            S3B_OK(upload_split(m->pos_w4, w4.data(), w4.size()));
+        }
         S3B_OK(upload_vec(m, "encoder.pos_conv.0.bias", D, m->pos_b));
     }
     S3B_OK(upload_vec(m, "encoder.layer_norm.weight", D, m->enc_ln_g));
@@ -575,6 +589,34 @@ static int posconv_params(GemmParams& p, const s3b_config& c, const __nv_bfloat1
     return 0;
 }
 
+// pos_conv with FOUR taps per k-block on CTA pairs: consecutive taps read the same activation rows shifted by one
+// frame, so the one-tap formulation (N = cpg = 48 columns) is bound by the shared-memory reads of its A operand
+// (4 KB per 24-cycle MMA). Writing tap = 4q + j,
+//     Z_j[u] = sum_q x[u + 4q - Kp/2] . W[4q + j],      conv[t] = sum_j Z_j[t + j]
+// gives one GEMM with N = 4*cpg (192 / 256) columns per group and Kp/4 k-blocks whose A rows advance by 4; the four
+// column blocks are re-aligned by posconv_combine_kernel (norm.cu). Rows u in [0, T+3) per utterance.
+static bool posconv4_ok(const s3b_config& c) {
+    const int cpg = c.embed_dim / c.pos_conv_groups;
+    return pairs_enabled() && c.pos_conv_kernel % 4 == 0 && (4 * cpg == 192 || 4 * cpg == 256) &&
+           getenv("S3B_POSCONV1") == nullptr;
+}
+static int posconv4_params(GemmParams& p, const s3b_config& c, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo,
+                           const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int B, int T) {
+    memset(&p, 0, sizeof(p));
+    const int D = c.embed_dim, G = c.pos_conv_groups, cpg = D / G, Kq = c.pos_conv_kernel / 4, un = 4 * cpg;
+    TMAP_OK(encode_tmap_bf16_3d(&p.a_hi, x_hi, D, T, B, D, (uint64_t)T * D, 64, 128));
+    TMAP_OK(encode_tmap_bf16_3d(&p.a_lo, x_lo, D, T, B, D, (uint64_t)T * D, 64, 128));
+    TMAP_OK(encode_tmap_bf16_3d(&p.b_hi, w_hi, 64, un, (uint64_t)G * Kq, 64, (uint64_t)un * 64, 64, un / 2));
+    TMAP_OK(encode_tmap_bf16_3d(&p.b_lo, w_lo, 64, un, (uint64_t)G * Kq, 64, (uint64_t)un * 64, 64, un / 2));
+    p.two_cta = 1;
+    p.batches = B, p.rows_per_batch = T + 3, p.tiles_m_per_batch = (T + 3 + 127) / 128;
+    p.n_tiles = G, p.umma_n = un, p.block_k = 64, p.num_k_blocks = Kq, p.kb_per_row = 1;
+    p.a_row_step = 4, p.a_row_off = -(c.pos_conv_kernel / 2), p.a_k_per_ntile = cpg, p.b_n_tiled = 0, p.b_z_per_ntile = Kq;
+    p.out_rows_per_batch = T + 3;
+    p.alg_flops = 2.0 * (double)B * T * D * cpg * c.pos_conv_kernel;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // launch accounting / profiling
 // ------------------------------------------------------------------------------------------------
@@ -725,17 +767,30 @@ static int forward_impl(s3b_model* m, const float* const* wavs_dev, const int64_
     float* hs0 = hidden_out;
     const size_t hs_stride = (size_t)M * D;
     {
-        S3B_OK(posconv_params(p, c, m->x_s.h(), m->x_s.l(), m->pos_w.h(), m->pos_w.l(), B, T));
-        Epi e;
-        e.bias = m->pos_b.as<float>();
-        e.gelu = 1;
-        e.residual = m->x_f32.as<float>();
-        e.out_f32 = c.layer_norm_first ? hs0 : m->tmp_f32.as<float>();
-        set_epi(p, e, D);
-        KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
-        if (!c.layer_norm_first)
-            KNORM(launch_layernorm(m->tmp_f32.as<float>(), (size_t)M, D, m->enc_ln_g.as<float>(),
-                                     m->enc_ln_b.as<float>(), 0, hs0, m->xs_s.h(), m->xs_s.l(), st));
+        if (posconv4_ok(c)) {
+            S3B_OK(m->pos_z.ensure((size_t)B * (T + 3) * 4 * D * sizeof(float)));
+            S3B_OK(posconv4_params(p, c, m->x_s.h(), m->x_s.l(), m->pos_w4.h(), m->pos_w4.l(), B, T));
+            Epi e;
+            e.out_f32 = m->pos_z.as<float>();
+            set_epi(p, e, 4 * D);
+            KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
+            const bool ln = !c.layer_norm_first;
+            KNORM(launch_posconv_combine(m->pos_z.as<float>(), m->x_f32.as<float>(), m->pos_b.as<float>(), B, T, D,
+                                           D / c.pos_conv_groups, m->enc_ln_g.as<float>(), m->enc_ln_b.as<float>(),
+                                           ln ? 1 : 0, hs0, ln ? m->xs_s.h() : nullptr, ln ? m->xs_s.l() : nullptr, st));
+        } else {
+            S3B_OK(posconv_params(p, c, m->x_s.h(), m->x_s.l(), m->pos_w.h(), m->pos_w.l(), B, T));
+            Epi e;
+            e.bias = m->pos_b.as<float>();
+            e.gelu = 1;
+            e.residual = m->x_f32.as<float>();
+            e.out_f32 = c.layer_norm_first ? hs0 : m->tmp_f32.as<float>();
+            set_epi(p, e, D);
+            KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
+            if (!c.layer_norm_first)
+                KNORM(launch_layernorm(m->tmp_f32.as<float>(), (size_t)M, D, m->enc_ln_g.as<float>(),
+                                         m->enc_ln_b.as<float>(), 0, hs0, m->xs_s.h(), m->xs_s.l(), st));
+        }
         if (layer_done) S3B_OK(layer_done(m, 0, st, user));
     }
 

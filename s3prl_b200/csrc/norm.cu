@@ -76,6 +76,105 @@ cudaError_t launch_layernorm(const float* x, size_t M, int D, const float* gamma
 }
 
 // ------------------------------------------------------------------------------------------------
+// pos_conv combine: the grouped k=128 convolution is computed as a GEMM over FOUR taps per k-block,
+//   Z_j[u] = sum_q x[u + 4q - 64] . W[4q + j]   (j = 0..3, N = 4 * cpg columns per group; model.cu posconv4_params)
+// and the four column blocks are re-aligned here:  conv[t] = sum_j Z_j[t + j]. One warp per frame:
+//   y = x + GELU(conv + bias)                      (wav2vec2_model.py:3064-3067)
+//   post-LN models: y -> LayerNorm -> hidden state 0 (fp32) + bf16 hi/lo   (wav2vec2_model.py:3069-3070)
+// z: [B][T + 3][G][4][cpg] fp32
+// ------------------------------------------------------------------------------------------------
+template <int V4>
+__global__ void __launch_bounds__(256) posconv_combine_kernel(const float* __restrict__ z, const float* __restrict__ x,
+                                                              const float* __restrict__ bias, int B, int T, int cpg,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, int do_ln,
+                                                              float* __restrict__ out_f32,
+                                                              __nv_bfloat16* __restrict__ out_hi,
+                                                              __nv_bfloat16* __restrict__ out_lo) {
+    constexpr int D = V4 * 128;
+    const int lane = threadIdx.x & 31;
+    const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    pdl_wait();
+    pdl_launch_dependents();
+    if (row >= (size_t)B * T) return;
+    const int b = (int)(row / T), t = (int)(row - (size_t)b * T);
+    const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+    const float4* b4 = reinterpret_cast<const float4*>(bias);
+    float4 v[V4];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+        const int c = 4 * (lane + 32 * i);
+        const int g = c / cpg, co = c - g * cpg;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 zz = __ldg(reinterpret_cast<const float4*>(
+                z + ((size_t)b * (T + 3) + t + j) * (size_t)(4 * D) + (size_t)g * 4 * cpg + j * cpg + co));
+            acc.x += zz.x, acc.y += zz.y, acc.z += zz.z, acc.w += zz.w;
+        }
+        const float4 bb = __ldg(b4 + lane + 32 * i), xx = xr[lane + 32 * i];
+        v[i].x = xx.x + gelu_erf(acc.x + bb.x);
+        v[i].y = xx.y + gelu_erf(acc.y + bb.y);
+        v[i].z = xx.z + gelu_erf(acc.z + bb.z);
+        v[i].w = xx.w + gelu_erf(acc.w + bb.w);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    float mean = 0.f, rstd = 1.f;
+    if (do_ln) {
+        mean = warp_sum(s) * (1.0f / D);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < V4; ++i) {
+            const float a = v[i].x - mean, bq = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            q += (a * a + bq * bq) + (c * c + d * d);
+        }
+        rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+    }
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+        const int c4 = lane + 32 * i;
+        float4 y = v[i];
+        if (do_ln) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+            const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+            y.x = (y.x - mean) * rstd * g.x + be.x;
+            y.y = (y.y - mean) * rstd * g.y + be.y;
+            y.z = (y.z - mean) * rstd * g.z + be.z;
+            y.w = (y.w - mean) * rstd * g.w + be.w;
+        }
+        if (out_f32 != nullptr) reinterpret_cast<float4*>(out_f32 + row * D)[c4] = y;
+        if (out_hi != nullptr) {
+            uint32_t h0, l0, h1, l1;
+            split_pack2(y.x, y.y, h0, l0);
+            split_pack2(y.z, y.w, h1, l1);
+            reinterpret_cast<uint2*>(out_hi + row * D)[c4] = make_uint2(h0, h1);
+            reinterpret_cast<uint2*>(out_lo + row * D)[c4] = make_uint2(l0, l1);
+        }
+    }
+}
+
+cudaError_t launch_posconv_combine(const float* z, const float* x, const float* bias, int B, int T, int D, int cpg,
+                                   const float* gamma, const float* beta, int do_ln, float* out_f32,
+                                   __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t s) {
+    const size_t M = (size_t)B * T;
+    if (M == 0) return cudaSuccess;
+    if (cpg % 4 != 0) return cudaErrorInvalidValue;
+    const unsigned blocks = (unsigned)((M + 7) / 8);
+#define S3B_PC(V)                                                                                                   \
+    return launch_pdl(posconv_combine_kernel<V>, dim3(blocks), dim3(256), 0, s, z, x, bias, B, T, cpg, gamma, beta, \
+                      do_ln, out_f32, out_hi, out_lo)
+    switch (D) {
+        case 512: S3B_PC(4);
+        case 768: S3B_PC(6);
+        case 1024: S3B_PC(8);
+        case 1280: S3B_PC(10);
+        default: return cudaErrorInvalidValue;
+    }
+#undef S3B_PC
+}
+
+// ------------------------------------------------------------------------------------------------
 // Featurizer weighted sum: streams NL layers once (vs. torch.stack + mul + sum = >= 3 passes)
 // ------------------------------------------------------------------------------------------------
 static constexpr int kMaxLayers = 64;
