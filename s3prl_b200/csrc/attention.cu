@@ -228,18 +228,20 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
                 for (int i = 0; i < kKBlk; ++i)
                     if (kbase + i >= kv_len) s[i] = -INFINITY;
             }
-            float mx = s[0];
+            float mx = fmaxf(s[0], s[1]);
 #pragma unroll
-            for (int i = 1; i < kKBlk; ++i) mx = fmaxf(mx, s[i]);
+            for (int i = 2; i < kKBlk; i += 2) mx = fmax3(mx, s[i], s[i + 1]);
             const float m_new = fmaxf(m_run, mx);  // finite: key kbase is always valid
             const float alpha = fast_exp2(m_run - m_new);
             float psum0 = 0.f, psum1 = 0.f;
             uint32_t hw[32], lw[32];
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                const float p0 = fast_exp2(s[2 * e] - m_new);
-                const float p1 = fast_exp2(s[2 * e + 1] - m_new);
-                psum0 += p0, psum1 += p1;
+            for (int e = 0; e < 32; ++e) {  // 10 instructions per key pair: FMNMX3 above, FADD2, 2 MUFU, FADD2, split (5)
+                float d0, d1;
+                fsub2(d0, d1, s[2 * e], s[2 * e + 1], m_new, m_new);
+                const float p0 = fast_exp2(d0);
+                const float p1 = fast_exp2(d1);
+                fadd2(psum0, psum1, psum0, psum1, p0, p1);
                 split_pack2(p0, p1, hw[e], lw[e]);
             }
             l_run = fmaf(l_run, alpha, psum0 + psum1);

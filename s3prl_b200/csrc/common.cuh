@@ -51,12 +51,32 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
     lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
+// Blackwell packed fp32 arithmetic (FADD2) and three-input max (FMNMX3): the softmax and split epilogues are
+// instruction-issue bound, these halve their add / max counts.
+__device__ __forceinline__ void fsub2(float& x, float& y, float a0, float a1, float b0, float b1) {
+    asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; sub.rn.f32x2 rd, ra, rb; "
+        "mov.b64 {%0, %1}, rd; }"
+        : "=f"(x), "=f"(y)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fadd2(float& x, float& y, float a0, float a1, float b0, float b1) {
+    asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rd, ra, rb; "
+        "mov.b64 {%0, %1}, rd; }"
+        : "=f"(x), "=f"(y)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
 // pack two floats -> two bf16x2 words (hi word, lo word); element 0 in the low half.
-// 6 instructions per pair: cvt.rn.bf16x2, shl, lop, 2 x fsub, cvt.rn.bf16x2
+// 5 instructions per pair: F2FP (cvt.rn.bf16x2), SHF, LOP3, FADD2 (both residuals), F2FP
 __device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
-    const float ra = a - __uint_as_float(hi << 16);
-    const float rb = b - __uint_as_float(hi & 0xffff0000u);
+    float ra, rb;
+    fsub2(ra, rb, a, b, __uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u));
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
 }
 

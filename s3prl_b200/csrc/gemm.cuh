@@ -57,6 +57,10 @@ struct GemmParams {
 
     double alg_flops;  // host-side accounting only: 2*M*N*K with the un-padded K
 
+    // CTA-pair kernel: 16-wide MMA k-steps issued per 64-wide k-block (0 = all 4). pos_conv with 48 channels per group
+    // loads 64-wide boxes but only the first 3 k-steps carry non-zero weights.
+    int k_steps;
+
     // debug timeline (tools/gemm_trace.py): 16 clock64 stamps of CTA 0, or nullptr
     unsigned long long* trace;
 };

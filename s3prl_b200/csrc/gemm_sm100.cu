@@ -532,6 +532,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
         // ===================== MMA issuer (leader CTA only) =====================
         if (elect_one()) {
             const uint32_t idesc = make_idesc_bf16(2 * kBlockM, (uint32_t)p.umma_n);
+            const int k_steps = p.k_steps > 0 ? p.k_steps : k2BlockK / 16;
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -552,10 +553,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
                     const uint64_t db_lo = make_smem_desc<128>(st + 3 * k2TileBytes);
 #pragma unroll
                     for (int k = 0; k < k2BlockK / 16; ++k) {
-                        const uint64_t ko = (uint64_t)(k * 2);
-                        umma_bf16_2cta(d_tmem, da_lo + ko, db_hi + ko, idesc, (kb | k) != 0 ? 1u : 0u);
-                        umma_bf16_2cta(d_tmem, da_hi + ko, db_lo + ko, idesc, 1u);
-                        umma_bf16_2cta(d_tmem, da_hi + ko, db_hi + ko, idesc, 1u);
+                        if (k < k_steps) {
+                            const uint64_t ko = (uint64_t)(k * 2);
+                            umma_bf16_2cta(d_tmem, da_lo + ko, db_hi + ko, idesc, (kb | k) != 0 ? 1u : 0u);
+                            umma_bf16_2cta(d_tmem, da_hi + ko, db_lo + ko, idesc, 1u);
+                            umma_bf16_2cta(d_tmem, da_hi + ko, db_hi + ko, idesc, 1u);
+                        }
                     }
                     umma_commit_2cta(&empty_bar[stage]);
                     if (++stage == k2Stages) stage = 0, phase ^= 1u;

@@ -613,6 +613,7 @@ static int posconv4_params(GemmParams& p, const s3b_config& c, const __nv_bfloat
     p.n_tiles = G, p.umma_n = un, p.block_k = 64, p.num_k_blocks = Kq, p.kb_per_row = 1;
     p.a_row_step = 4, p.a_row_off = -(c.pos_conv_kernel / 2), p.a_k_per_ntile = cpg, p.b_n_tiled = 0, p.b_z_per_ntile = Kq;
     p.out_rows_per_batch = T + 3;
+    p.k_steps = (cpg + 15) / 16;  // 48 channels per group: the 4th k-step of every 64-wide box has zero weights
     p.alg_flops = 2.0 * (double)B * T * D * cpg * c.pos_conv_kernel;
     return 0;
 }

@@ -27,6 +27,8 @@ def launches(path):
     for r in rows[start + 1:]:
         if len(r) <= vi:
             continue
+        if "Metric Name" in hdr and r[hdr.index("Metric Name")] != "gpu__time_duration.sum":
+            continue  # CSVs that also carry DRAM byte counters (tools/ncu_traffic.py reads those)
         v = float(r[vi].replace(",", ""))
         v = v / 1000.0 if r[ui] == "ns" else (v * 1000.0 if r[ui] == "ms" else v)
         a = agg.setdefault(r[ki].split("(")[0], [0, 0.0])
