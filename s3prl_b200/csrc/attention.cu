@@ -3,7 +3,7 @@
 // (s3prl/upstream/wav2vec2/wav2vec2_model.py:1146-1168) and, when bias_table is given, WavLM's gated
 // relative-position bias (s3prl/upstream/wavlm/modules.py:511-580).
 //
-// One CTA = one (batch, head, 128-query tile), 192 threads:
+// One CTA = one (batch, head, 128-query tile), 192 threads (kHalves = 1):
 //   warps 0..3 : softmax warps, thread i owns query row i (TMEM lane i)
 //   warp 4     : S warp  (one elected lane): Q/K TMA loads, S_j = Q K_j^T
 //   warp 5     : PV warp (one elected lane): V TMA loads, O += P_j V_j
@@ -36,10 +36,28 @@ static constexpr int kOffK = 2 * kQBytes;
 static constexpr int kStage = 2 * kKBytes;  // one K (or V^T) block, hi + lo planes
 static constexpr int kOffV = kOffK + 2 * kStage;
 static constexpr int kOffBar = kOffV + 2 * kStage;
-static constexpr int kAttnSmem = kOffBar + 128 + 1024;  // 99,456 B; two CTAs per SM (TMEM: 2 x 256 columns)
+// A query row can be shared by kHalves softmax threads (warps w and w + 4 own the same TMEM lane quadrant): thread
+// (row, half) handles 64 / kHalves keys of every block and 64 / kHalves columns of O; the row maximum is exchanged
+// once per block through shared memory (named barrier per lane quadrant), the row sums stay per-thread partials
+// until the end. Measured (same-box A/B, both variants pass the parity tests): 2 threads per row = 1 thread per
+// row within 0.5 % — the ~1800-cycle period per 64-key block is set by the two co-resident CTAs' MMAs (12 S MMAs
+// that re-read Q from shared memory at 192 B/clk + 12 PV MMAs ~ 960 cycles per block and CTA), not by the softmax
+// instruction stream — so the default stays 1 (192 threads).
+#ifndef S3B_ATTN_HALVES
+#define S3B_ATTN_HALVES 1
+#endif
+static constexpr int kHalves = S3B_ATTN_HALVES;
+static constexpr int kSmWarps = 4 * kHalves;
+static constexpr int kCols = kKBlk / kHalves;  // score columns per softmax thread
+static constexpr int kDCols = kHd / kHalves;   // O columns per softmax thread
+static constexpr int kOffX = kOffBar + 128;    // float [2][2][128] row-max exchange
+static constexpr int kAttnSmem = kOffX + 2048 + 1024;  // ~101.5 KB; two CTAs per SM (TMEM: 2 x 256 columns)
 static constexpr int kTmemCols = 256;
 static constexpr uint32_t kColO = 128, kColPhi = 192, kColPlo = 224;
-static constexpr int kAttnThreads = 192;
+static constexpr int kAttnThreads = 32 * (kSmWarps + 2);
+
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t (&v)[32]) { tmem_st_32x32(taddr, v); }
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t (&v)[16]) { tmem_st_32x16(taddr, v); }
 
 template <bool kBias>
 __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid_constant__ AttnParams p) {
@@ -72,12 +90,12 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
         mbar_init(&bar_s[0], 1);
         mbar_init(&bar_s[1], 1);
         mbar_init(bar_pv, 1);
-        mbar_init(bar_p, 4);
-        mbar_init(&bar_sfree[0], 4);
-        mbar_init(&bar_sfree[1], 4);
+        mbar_init(bar_p, kSmWarps);
+        mbar_init(&bar_sfree[0], kSmWarps);
+        mbar_init(&bar_sfree[1], kSmWarps);
         fence_mbar_init();
     }
-    if (warp == 4) {
+    if (warp == kSmWarps) {
         if (lane == 0) {
             tma_prefetch_desc(&p.q_hi);
             tma_prefetch_desc(&p.k_hi);
@@ -102,7 +120,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
         if (tracing && (j) < 16) p.trace[((role)*16 + (j)) * 8 + (slot)] = clock64(); \
     } while (0)
 
-    if (warp == 4) {
+    if (warp == kSmWarps) {
         // ===================== S warp: Q/K loads + S_j = Q K_j^T =====================
         if (elect_one()) {
             const uint32_t idesc = make_idesc_bf16(kQTile, 64);
@@ -146,7 +164,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
                 S3B_TR(0, j, 3);
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == kSmWarps + 1) {
         // ===================== PV warp: V loads + O += P_j V_j =====================
         if (elect_one()) {
             const uint32_t idesc = make_idesc_bf16(kQTile, 64);
@@ -185,9 +203,13 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
         }
     } else {
         // ===================== softmax warps =====================
-        const uint32_t lane_off = ((uint32_t)(warp * 32)) << 16;
-        const int q_row = q0 + tid;
+        const int quad = warp & 3;   // TMEM lane quadrant
+        const int half = warp >> 2;  // which key / O-column share of the row
+        const int row_in_tile = quad * 32 + lane;
+        const uint32_t lane_off = ((uint32_t)(quad * 32)) << 16;
+        const int q_row = q0 + row_in_tile;
         const bool row_ok = q_row < p.T;
+        float* xch = reinterpret_cast<float*>(smem + kOffX);
         float gate = 0.f;
         const float* brow = nullptr;
         if (kBias) {
@@ -195,48 +217,57 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
             brow = p.bias_table + (size_t)h * (2 * p.T - 1) + (p.T - 1 - (row_ok ? q_row : 0));  // index by key k
         }
         float m_run = -INFINITY;  // running row max (log2 domain)
-        float l_run = 0.f;
+        float l_run = 0.f;        // this thread's share of the row sum
 
         for (int j = 0; j < nblk; ++j) {
             mbar_wait(&bar_s[j & 1], (uint32_t)((j >> 1) & 1));
             __syncwarp();
             tc_fence_after();
             if (tid == 0) S3B_TR(1, j, 0);
-            float s[kKBlk];
+            float s[kCols];
             {
-                const uint32_t ts = tmem_base + (uint32_t)(j & 1) * 64u + lane_off;
-                uint32_t v0[32], v1[32];
-                tmem_ld_32x32(ts, v0);
-                tmem_ld_32x32(ts + 32, v1);
-                tmem_ld_wait();
+                const uint32_t ts = tmem_base + (uint32_t)(j & 1) * 64u + lane_off + (uint32_t)(half * kCols);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(v0[i]), s[32 + i] = __uint_as_float(v1[i]);
+                for (int c = 0; c < kCols; c += 32) {
+                    uint32_t v0[32];
+                    tmem_ld_32x32(ts + (uint32_t)c, v0);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) s[c + i] = __uint_as_float(v0[i]);
+                }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_sfree[j & 1]);  // the S warp may overwrite this buffer with S_{j+2}
-            const int kbase = j * kKBlk;
+            const int kbase = j * kKBlk + half * kCols;
             if (kBias) {
 #pragma unroll
-                for (int i = 0; i < kKBlk; ++i) {
+                for (int i = 0; i < kCols; ++i) {
                     const int kk = kbase + i;
                     s[i] = fmaf(gate, (kk < p.T) ? __ldg(brow + kk) : 0.f, s[i]);
                 }
             }
-            if (kbase + kKBlk > kv_len) {  // block-uniform: only the last block is partially masked
+            if (j * kKBlk + kKBlk > kv_len) {  // block-uniform: only the last block is partially masked
 #pragma unroll
-                for (int i = 0; i < kKBlk; ++i)
+                for (int i = 0; i < kCols; ++i)
                     if (kbase + i >= kv_len) s[i] = -INFINITY;
             }
             float mx = fmaxf(s[0], s[1]);
 #pragma unroll
-            for (int i = 2; i < kKBlk; i += 2) mx = fmax3(mx, s[i], s[i + 1]);
-            const float m_new = fmaxf(m_run, mx);  // finite: key kbase is always valid
+            for (int i = 2; i < kCols; i += 2) mx = fmax3(mx, s[i], s[i + 1]);
+            if constexpr (kHalves == 2) {
+                // double-buffered by block parity: the partner reads buffer j&1 before it reaches the barrier of
+                // block j+1, and this thread rewrites it only in block j+2
+                xch[((j & 1) * 2 + half) * 128 + row_in_tile] = mx;
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+                mx = fmaxf(mx, xch[((j & 1) * 2 + (half ^ 1)) * 128 + row_in_tile]);
+            }
+            const float m_new = fmaxf(m_run, mx);  // finite: key j*64 is always valid
             const float alpha = fast_exp2(m_run - m_new);
             float psum0 = 0.f, psum1 = 0.f;
-            uint32_t hw[32], lw[32];
+            uint32_t hw[kCols / 2], lw[kCols / 2];
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {  // 10 instructions per key pair: FMNMX3 above, FADD2, 2 MUFU, FADD2, split (5)
+            for (int e = 0; e < kCols / 2; ++e) {  // 10 instructions per key pair: FMNMX3 above, FADD2, 2 MUFU, FADD2, split (5)
                 float d0, d1;
                 fsub2(d0, d1, s[2 * e], s[2 * e + 1], m_new, m_new);
                 const float p0 = fast_exp2(d0);
@@ -256,18 +287,20 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
                 if (tid == 0) S3B_TR(1, j, 2);
                 if (!__all_sync(0xffffffffu, alpha == 1.0f)) {  // some row's max moved: rescale O in place
 #pragma unroll
-                    for (int c = 0; c < kHd; c += 32) {
+                    for (int c = 0; c < kDCols; c += 32) {
                         uint32_t v[32];
-                        tmem_ld_32x32(tmem_o + lane_off + (uint32_t)c, v);
+                        const uint32_t ta = tmem_o + lane_off + (uint32_t)(half * kDCols + c);
+                        tmem_ld_32x32(ta, v);
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-                        tmem_st_32x32(tmem_o + lane_off + (uint32_t)c, v);
+                        tmem_st_32x32(ta, v);
                     }
                 }
             }
-            tmem_st_32x32(tmem_base + lane_off + kColPhi, hw);
-            tmem_st_32x32(tmem_base + lane_off + kColPlo, lw);
+            // packed bf16 pairs: key 2c, 2c+1 of the block in column c of the P_hi / P_lo planes
+            tmem_st_cols(tmem_base + lane_off + kColPhi + (uint32_t)(half * (kCols / 2)), hw);
+            tmem_st_cols(tmem_base + lane_off + kColPlo + (uint32_t)(half * (kCols / 2)), lw);
             tmem_st_wait();     // P_j and the rescaled O are in tensor memory
             tc_fence_before();  // orders this thread's tcgen05.ld / tcgen05.st before the hand-off
             __syncwarp();
@@ -279,12 +312,19 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
         mbar_wait(bar_pv, (uint32_t)((nblk - 1) & 1));
         __syncwarp();
         tc_fence_after();
-        const float inv = 1.0f / l_run;
-        const size_t off = ((size_t)b * p.T + (row_ok ? q_row : 0)) * (size_t)p.D + (size_t)h * kHd;
+        float l_tot = l_run;
+        if constexpr (kHalves == 2) {
+            // buffer nblk&1 was last read in block nblk-2, which the partner left before the barrier of block nblk-1
+            xch[((nblk & 1) * 2 + half) * 128 + row_in_tile] = l_run;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+            l_tot += xch[((nblk & 1) * 2 + (half ^ 1)) * 128 + row_in_tile];
+        }
+        const float inv = 1.0f / l_tot;
+        const size_t off = ((size_t)b * p.T + (row_ok ? q_row : 0)) * (size_t)p.D + (size_t)h * kHd + half * kDCols;
 #pragma unroll
-        for (int c = 0; c < kHd; c += 32) {
+        for (int c = 0; c < kDCols; c += 32) {
             uint32_t v[32];
-            tmem_ld_32x32(tmem_o + lane_off + (uint32_t)c, v);
+            tmem_ld_32x32(tmem_o + lane_off + (uint32_t)(half * kDCols + c), v);
             tmem_ld_wait();
             if (row_ok) {
                 uint4* dh = reinterpret_cast<uint4*>(p.ctx_hi + off + c);
@@ -305,7 +345,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == kSmWarps) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }
