@@ -337,7 +337,7 @@ def run_ours(args):
         },
         "whole_step_tflops": flops_utt * GLOBAL_BATCH / world / 1e12 / (ms_step * 1e-3) * world,
         "roofline": {
-            "kernel": "gemm_bf16x3_kernel (tcgen05, all GEMM launches of a step)", "bound": "tensor",
+            "kernel": "gemm2_bf16x3_kernel (tcgen05 cta_group::2, all GEMM launches of a step)", "bound": "tensor",
             "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tflops / peak_tf,
             "traffic": gemm_traffic(), "peak_source": peak_src,
             "mma_pipe_tflops": 3.0 * gemm_tflops,
