@@ -39,6 +39,7 @@ CASES = {
     "wav2vec2_large_960": ([[12000, 7001]], 13),
     "wavlm_large": ([[12000, 7001]], 13),
     "hubert_large_ll60k": ([[12000, 7001]], 13),
+    "unispeech_sat_base_plus": ([[16000, 12345, 800], [8000, 8000]], 7),
 }
 
 
@@ -98,12 +99,15 @@ def reference_expert(name: str, sd):
             full.update(sd)
             torch.save({"task_cfg": task_cfg, "model_cfg": model_cfg, "model_weight": full}, tmp.name)
         else:
-            from s3prl.upstream.wavlm.expert import UpstreamExpert
+            if name.startswith("unispeech_sat"):
+                from s3prl.upstream.unispeech_sat.expert import UpstreamExpert
+            else:
+                from s3prl.upstream.wavlm.expert import UpstreamExpert
             from s3prl.upstream.wavlm.WavLM import WavLM, WavLMConfig
 
             model_cfg.update(
                 normalize=cfg.normalize,
-                relative_position_embedding=True,
+                relative_position_embedding=cfg.relative_position_embedding,
                 num_buckets=cfg.num_buckets,
                 max_distance=cfg.max_distance,
                 gru_rel_pos=cfg.gru_rel_pos,

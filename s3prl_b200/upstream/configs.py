@@ -54,13 +54,34 @@ ARCHS: Dict[str, ArchConfig] = {
     "wavlm_base": replace(_BASE, **_WAVLM),
     "wavlm_base_plus": replace(_BASE, **_WAVLM),
     "wavlm_large": replace(_BASE, **_WAVLM, **_LL60K),
+    # UniSpeech-SAT runs the WavLM model class without relative position bias
+    # (s3prl/upstream/unispeech_sat/expert.py:20,37-38; hubconf.py:47-82)
+    "unispeech_sat_base": replace(_BASE, family="wavlm"),
+    "unispeech_sat_base_plus": replace(_BASE, family="wavlm"),
+    "unispeech_sat_large": replace(_BASE, family="wavlm", **_LL60K),
 }
+# Same-skeleton relatives: identical architecture, different pre-training data (only the checkpoint differs).
+for _alias, _arch in {
+    # s3prl/upstream/wav2vec2/hubconf.py:123-160
+    "wav2vec2_large_lv60_cv_swbd_fsh": "wav2vec2_large_ll60k",
+    "xlsr_53": "wav2vec2_large_ll60k",
+    "xls_r_300m": "wav2vec2_large_ll60k",
+    # s3prl/upstream/hubert/hubconf.py:111-156
+    "hubert_base_robust_mgr": "hubert_base",
+    "mhubert_base_vp_en_es_fr_it3": "hubert_base",
+    "contentvec": "hubert_base",
+    "contentvec_km100": "hubert_base",
+    "contentvec_km500": "hubert_base",
+    "ms_hubert": "hubert_base",
+}.items():
+    ARCHS[_alias] = ARCHS[_arch]
 ALIASES = {
     "hubert": "hubert_base",
     "hubert_large": "hubert_large_ll60k",
     "wav2vec2": "wav2vec2_base_960",
     "wav2vec2_large": "wav2vec2_large_960",
     "wavlm": "wavlm_base",
+    "unispeech_sat": "unispeech_sat_base_plus",
 }
 
 

@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 
 from .. import lib as _lib
-from .configs import DOWNSAMPLE_RATE, ArchConfig, get_arch
+from .configs import ALIASES, ARCHS, DOWNSAMPLE_RATE, ArchConfig, get_arch
 from .weights import fabricate_state_dict, load_reference_checkpoint
 
 SAMPLE_RATE = 16000
@@ -223,6 +223,10 @@ class UpstreamExpert(nn.Module):
 
 
 def _family_of(name: str) -> str:
+    if name in ARCHS or name in ALIASES:
+        return get_arch(name).family
+    if name.startswith("unispeech_sat"):  # the WavLM model class (s3prl/upstream/unispeech_sat/expert.py:20)
+        return "wavlm"
     for fam in ("hubert", "wav2vec2", "wavlm"):
         if name.startswith(fam):
             return fam

@@ -93,6 +93,31 @@ def test_hub_injection_into_reference():
     assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
 
 
+def test_hub_covers_the_same_skeleton_relatives():
+    """Every wav2vec2 / HuBERT / WavLM / UniSpeech-SAT hub entry of the reference whose model is the 7-conv +
+    post-/pre-LN Transformer skeleton with 64-wide heads has an entry here with the right family and
+    shape; the entries outside the skeleton (conformer, 1B/2B XLS-R with 80/120-wide heads) are absent on purpose."""
+    from s3prl_b200 import hub
+    from s3prl_b200.upstream.configs import get_arch
+
+    names = set(hub.options())
+    for n in ("hubert_base", "hubert_large_ll60k", "hubert_base_robust_mgr", "mhubert_base_vp_en_es_fr_it3",
+              "contentvec", "contentvec_km100", "contentvec_km500", "ms_hubert", "wav2vec2_base_960",
+              "wav2vec2_large_960", "wav2vec2_large_ll60k", "wav2vec2_large_lv60_cv_swbd_fsh", "xlsr_53",
+              "xls_r_300m", "wavlm_base", "wavlm_base_plus", "wavlm_large", "unispeech_sat_base",
+              "unispeech_sat_base_plus", "unispeech_sat_large", "hubert_local", "wav2vec2_local", "wavlm_local",
+              "unispeech_sat_local", "fbank", "mel", "linear"):
+        assert n in names, n
+    for n in ("xls_r_1b", "xls_r_2b", "wav2vec2_conformer_relpos"):
+        assert n not in names
+    assert get_arch("xlsr_53") == get_arch("wav2vec2_large_ll60k")
+    u = get_arch("unispeech_sat_base_plus")
+    assert u.family == "wavlm" and not u.relative_position_embedding and not u.gru_rel_pos
+    ul = get_arch("unispeech_sat_large")
+    assert ul.layer_norm_first and ul.extractor_mode == "layer_norm" and ul.encoder_layers == 24
+    assert get_arch("unispeech_sat") == u
+
+
 def _gloo_worker(rank, world, port, tmpdir):
     import torch.distributed as dist
 
