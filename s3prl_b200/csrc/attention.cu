@@ -241,10 +241,15 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
             if (lane == 0) mbar_arrive(&bar_sfree[j & 1]);  // the S warp may overwrite this buffer with S_{j+2}
             const int kbase = j * kKBlk + half * kCols;
             if (kBias) {
+                if (kbase + kCols <= p.T) {  // block-uniform: every key of the block has a table entry
 #pragma unroll
-                for (int i = 0; i < kCols; ++i) {
-                    const int kk = kbase + i;
-                    s[i] = fmaf(gate, (kk < p.T) ? __ldg(brow + kk) : 0.f, s[i]);
+                    for (int i = 0; i < kCols; ++i) s[i] = fmaf(gate, __ldg(brow + kbase + i), s[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < kCols; ++i) {
+                        const int kk = kbase + i;
+                        s[i] = fmaf(gate, (kk < p.T) ? __ldg(brow + kk) : 0.f, s[i]);
+                    }
                 }
             }
             if (j * kKBlk + kKBlk > kv_len) {  // block-uniform: only the last block is partially masked

@@ -52,32 +52,43 @@ cudaError_t launch_wavlm_rel_table(const float* emb, int num_buckets, int max_di
     return e;
 }
 
-// one thread per (token, head): 64 inputs -> 8 outputs -> 2 gates; grep_linear (8 x 64 + 8) staged in smem
+// eight lanes per (token, head): 64 inputs -> 8 outputs -> 2 gates. The reference sums the 8 grep_linear outputs in two
+// groups of four before the sigmoids (modules.py:541-546: view(..., 2, 4).sum(-1)), so only the two summed weight
+// rows (and summed biases) are needed: 2 x 64 FMAs per thread instead of 8 x 64 (same value up to fp32 summation
+// order). The two combined rows are built in shared memory by every block.
 __global__ void __launch_bounds__(256) wavlm_gate_kernel(const __nv_bfloat16* __restrict__ x_hi,
                                                          const __nv_bfloat16* __restrict__ x_lo, size_t M, int T,
                                                          int H, int D, const float* __restrict__ gw,
                                                          const float* __restrict__ gb, const float* __restrict__ ga,
                                                          float* __restrict__ gate) {
-    __shared__ float sw[8 * 64 + 8];
-    if (gw != nullptr)
-        for (int i = threadIdx.x; i < 8 * 64 + 8; i += blockDim.x) sw[i] = i < 512 ? gw[i] : gb[i - 512];
+    __shared__ __align__(16) float sw[2 * 64 + 2];
+    if (gw != nullptr && threadIdx.x < 130) {
+        const int i = threadIdx.x;
+        if (i < 128) {
+            const int g = i >> 6, c = i & 63;
+            sw[i] = (gw[(4 * g) * 64 + c] + gw[(4 * g + 1) * 64 + c]) + (gw[(4 * g + 2) * 64 + c] + gw[(4 * g + 3) * 64 + c]);
+        } else {
+            const int g = i - 128;
+            sw[i] = (gb[4 * g] + gb[4 * g + 1]) + (gb[4 * g + 2] + gb[4 * g + 3]);
+        }
+    }
     __syncthreads();
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= M * (size_t)H) return;
-    const size_t m = idx / H;
-    const int h = (int)(idx - m * H);
+    // eight lanes per (token, head): lane c loads the c-th 16-byte chunk of the hi and lo planes, so a warp load covers
+    // four contiguous 128-byte head rows (one thread per head made every load touch 32 different lines)
+    const size_t gidx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t idx = gidx >> 3;
+    const int c = (int)(gidx & 7);
+    const bool ok = idx < M * (size_t)H;
+    const size_t m = ok ? idx / H : 0;
+    const int h = ok ? (int)(idx - m * H) : 0;
     const int b = (int)(m / T), t = (int)(m - (size_t)b * T);
     float g1 = 1.0f;
-    if (gw != nullptr) {
-        const size_t off = m * (size_t)D + (size_t)h * 64;
-        const uint4* ph = reinterpret_cast<const uint4*>(x_hi + off);
-        const uint4* pl = reinterpret_cast<const uint4*>(x_lo + off);
-        float u[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) u[j] = sw[512 + j];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {  // 8 bf16 per 16-byte chunk
-            const uint4 vh = ph[c], vl = pl[c];
+    if (gw != nullptr) {  // kernel-uniform
+        float sa = 0.f, sb = 0.f;
+        if (ok) {
+            const size_t off = m * (size_t)D + (size_t)h * 64;
+            const uint4 vh = reinterpret_cast<const uint4*>(x_hi + off)[c];
+            const uint4 vl = reinterpret_cast<const uint4*>(x_lo + off)[c];
             const uint32_t wh[4] = {vh.x, vh.y, vh.z, vh.w}, wl[4] = {vl.x, vl.y, vl.z, vl.w};
             float xv[8];
 #pragma unroll
@@ -85,25 +96,32 @@ __global__ void __launch_bounds__(256) wavlm_gate_kernel(const __nv_bfloat16* __
                 xv[2 * e] = __uint_as_float(wh[e] << 16) + __uint_as_float(wl[e] << 16);
                 xv[2 * e + 1] = __uint_as_float(wh[e] & 0xffff0000u) + __uint_as_float(wl[e] & 0xffff0000u);
             }
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-#pragma unroll
-                for (int e = 0; e < 8; ++e) u[j] = fmaf(sw[j * 64 + c * 8 + e], xv[e], u[j]);
+            const float4* w0 = reinterpret_cast<const float4*>(sw);
+            const float4* w1 = reinterpret_cast<const float4*>(sw + 64);
+            const float4 a0 = w0[2 * c], a1 = w0[2 * c + 1], b0 = w1[2 * c], b1 = w1[2 * c + 1];
+            sa = fmaf(a0.x, xv[0], sa), sa = fmaf(a0.y, xv[1], sa), sa = fmaf(a0.z, xv[2], sa), sa = fmaf(a0.w, xv[3], sa);
+            sa = fmaf(a1.x, xv[4], sa), sa = fmaf(a1.y, xv[5], sa), sa = fmaf(a1.z, xv[6], sa), sa = fmaf(a1.w, xv[7], sa);
+            sb = fmaf(b0.x, xv[0], sb), sb = fmaf(b0.y, xv[1], sb), sb = fmaf(b0.z, xv[2], sb), sb = fmaf(b0.w, xv[3], sb);
+            sb = fmaf(b1.x, xv[4], sb), sb = fmaf(b1.y, xv[5], sb), sb = fmaf(b1.z, xv[6], sb), sb = fmaf(b1.w, xv[7], sb);
         }
-        const float sa = (u[0] + u[1]) + (u[2] + u[3]);
-        const float sb = (u[4] + u[5]) + (u[6] + u[7]);
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, o);
+            sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        }
+        sa += sw[128], sb += sw[129];
         const float a = 1.0f / (1.0f + expf(-sa));
         const float bb = 1.0f / (1.0f + expf(-sb));
         g1 = a * (bb * ga[h] - 1.0f) + 2.0f;
     }
-    gate[((size_t)b * H + h) * T + t] = g1;
+    if (ok && c == 0) gate[((size_t)b * H + h) * T + t] = g1;
 }
 
 cudaError_t launch_wavlm_gate(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, size_t M, int B, int T, int H,
                               int D, const float* grep_w, const float* grep_b, const float* grep_a, float* gate,
                               cudaStream_t s) {
     (void)B;
-    const size_t n = M * (size_t)H;
+    const size_t n = M * (size_t)H * 8;  // eight lanes per (token, head)
     const unsigned blocks = (unsigned)((n + 255) / 256);
     wavlm_gate_kernel<<<blocks, 256, 0, s>>>(x_hi, x_lo, M, T, H, D, grep_w, grep_b, grep_a, gate);
     return cudaGetLastError();
