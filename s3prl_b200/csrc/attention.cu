@@ -8,7 +8,7 @@
 //   warp 4     : S warp  (one elected lane): Q/K TMA loads, S_j = Q K_j^T
 //   warp 5     : PV warp (one elected lane): V TMA loads, O += P_j V_j
 //   (one control warp doing both serialised ~2400 cycles of barrier waits + MMA issue per block)
-// Two CTAs are co-resident per SM (<= 168 registers/thread, ~97 KB smem, 256 TMEM columns each).
+// Two CTAs are co-resident per SM (<= 168 registers/thread, ~101 KB smem, 256 TMEM columns each).
 // TMEM columns: S0 [0,64) | S1 [64,128) | O [128,192) | P_hi [192,224) | P_lo [224,256).
 // Per 64-key block j:
 //   S_j = Qhi*Khi^T + Qhi*Klo^T + Qlo*Khi^T     tcgen05.mma M=128 N=64 K=64, as soon as its S buffer is free
