@@ -40,6 +40,7 @@ CASES = {
     "wavlm_large": ([[12000, 7001]], 13),
     "hubert_large_ll60k": ([[12000, 7001]], 13),
     "unispeech_sat_base_plus": ([[16000, 12345, 800], [8000, 8000]], 7),
+    "unispeech_sat_large": ([[12000, 7001]], 13),
 }
 
 
