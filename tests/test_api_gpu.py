@@ -57,3 +57,40 @@ def test_s3prl_upstream_wrapper(s3b_lib):
     assert all_lens[0].tolist() == O.s3prl_upstream_lengths(lens.tolist())
     assert all_hs[0].shape == (3, 50, 768)  # len(range(0, 16000, 320)) == 50: last frame repeated once
     assert torch.equal(all_hs[3][:, 49], all_hs[3][:, 48])
+
+
+def test_frozen_upstream_ctc_training_steps(s3b_lib):
+    """The SUPERB recipe of BASELINE config 5 in miniature (s3prl/downstream/runner.py:293-330, ctc/expert.py:64-108):
+    frozen upstream under no_grad, trainable Featurizer weights + a linear CTC head, synthetic LibriSpeech-shaped
+    batch. The loss must fall and the Featurizer's layer weights must move (gradient through s3b_weighted_sum_backward)."""
+    import torch.nn.functional as F
+    from torch.nn.utils.rnn import pad_sequence
+
+    from s3prl_b200.hub import hubert_base
+    from s3prl_b200.upstream.featurizer import Featurizer
+
+    torch.manual_seed(0)
+    up = hubert_base().to("cuda")
+    feat = Featurizer(up, "hidden_states", upstream_device="cuda").to("cuda")
+    head = torch.nn.Linear(feat.output_dim, 32).cuda()
+    opt = torch.optim.Adam(list(feat.parameters()) + list(head.parameters()), lr=3e-3)
+    g = torch.Generator().manual_seed(11)
+    wavs = [torch.randn(n, generator=g).cuda() for n in (24000, 17000, 9000)]
+    labels = [torch.randint(1, 32, (6,), generator=g) for _ in wavs]
+    w0 = feat.weights.detach().clone()
+    losses = []
+    for _ in range(8):
+        with torch.no_grad():  # runner.py:300-304: upstream frozen
+            res = up(wavs)
+        feats = feat(wavs, res)  # list of [T_i, D]
+        lens = torch.tensor([f.shape[0] for f in feats])
+        logp = F.log_softmax(head(pad_sequence(feats, batch_first=True)), dim=-1).transpose(0, 1)
+        loss = F.ctc_loss(logp, pad_sequence(labels, batch_first=True), lens, torch.tensor([6] * len(wavs)), blank=0,
+                          zero_infinity=True)
+        opt.zero_grad()
+        loss.backward()
+        assert feat.weights.grad is not None and torch.isfinite(feat.weights.grad).all()
+        opt.step()
+        losses.append(loss.item())
+    assert losses[-1] < 0.8 * losses[0], losses
+    assert (feat.weights.detach() - w0).abs().max().item() > 1e-4
