@@ -93,6 +93,29 @@ def test_hub_injection_into_reference():
     assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
 
 
+def test_header_is_plain_c_and_links(s3b_lib, tmp_path):
+    """include/s3prl_b200.h compiles as C99 (-Wall -Werror) and every entry point links from a plain-C program
+    (examples/cabi_smoke.c); the integer frame rule runs through the ABI without a GPU."""
+    import shutil
+    import subprocess
+
+    from s3prl_b200 import lib as L
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    exe = tmp_path / "cabi_smoke"
+    libdir = L.lib_path().parent
+    r = subprocess.run(
+        [gcc, "-std=c99", "-Wall", "-Werror", f"-I{ROOT / 'include'}", str(ROOT / "examples" / "cabi_smoke.c"),
+         f"-L{libdir}", "-ls3prl_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)],
+        capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    assert "23 entry points" in r.stdout and "49 3" in r.stdout
+
+
 def test_hub_covers_the_same_skeleton_relatives():
     """Every wav2vec2 / HuBERT / WavLM / UniSpeech-SAT hub entry of the reference whose model is the 7-conv +
     post-/pre-LN Transformer skeleton with 64-wide heads has an entry here with the right family and
