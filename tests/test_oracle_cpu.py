@@ -111,3 +111,33 @@ def test_gelu_formula():
     assert np.abs(out - ref).max() < 1e-6
     torch_fp32 = torch.nn.functional.gelu(torch.from_numpy(x)).numpy()
     assert np.abs(out - ref).max() <= np.abs(torch_fp32 - ref).max()  # at least as close to exact as torch's fp32 GELU
+
+
+def test_native_integer_rules_property(s3b_lib):
+    """Randomised (hypothesis) agreement of the C++ frame bookkeeping with the oracle's mask construction (which is
+    pinned to the reference by integer_rules.pt): ragged batches, boundary lengths around multiples of 320 and of the
+    400-sample receptive field, single-utterance batches, all three mask rules."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from s3prl_b200.upstream.expert import UpstreamExpert
+
+    experts = {
+        "hubert": UpstreamExpert(name="hubert_base", state_dict={}),
+        "wav2vec2": UpstreamExpert(name="wav2vec2_base_960", state_dict={}),
+        "wavlm": UpstreamExpert(name="wavlm_base_plus", state_dict={}),
+    }
+    length = st.one_of(
+        st.integers(min_value=400, max_value=200000),
+        st.builds(lambda k, d: max(400, 320 * k + d), st.integers(1, 600), st.integers(-3, 83)),
+    )
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.lists(length, min_size=1, max_size=6))
+    def check(lens):
+        T = O.conv_output_length(max(lens))
+        assert s3b_lib.s3b_num_frames(None, max(lens)) == T
+        for fam, ex in experts.items():
+            assert ex.valid_frames(lens) == O.valid_frames(fam, lens, max(lens)), (fam, lens)
+
+    check()
