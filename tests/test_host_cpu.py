@@ -93,6 +93,13 @@ def test_hub_injection_into_reference():
     assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
 
 
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under s3prl_b200/ (Python or CUDA) may import, include or execute it."""
+    pat = re.compile(r"^\s*(from|import)\s+\S*oracle|sys\.path\S*oracle|#include\s+\S*oracle", re.M)
+    for f in list((ROOT / "s3prl_b200").rglob("*.py")) + list((ROOT / "s3prl_b200" / "csrc").glob("*.cu*")):
+        assert not pat.search(f.read_text()), f
+
+
 def test_header_is_plain_c_and_links(s3b_lib, tmp_path):
     """include/s3prl_b200.h compiles as C99 (-Wall -Werror) and every entry point links from a plain-C program
     (examples/cabi_smoke.c); the integer frame rule runs through the ABI without a GPU."""
