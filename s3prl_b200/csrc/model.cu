@@ -936,20 +936,40 @@ extern "C" int s3b_forward_host(s3b_model* m, const float* const* wavs, const in
         ptrs[b] = d;
         off += (size_t)lens[b];
     }
-    // device->host copy of hidden state l overlaps the computation of layer l+1 (second stream)
+    // device->host copy of hidden state l overlaps the computation of layer l+1 (second stream).
+    // S3B_HOST_CHUNKS=k (experimental, default 1 = the whole batch at once): the batch is processed as k utterance
+    // chunks so that chunk c+1's conv stack overlaps chunk c's copies — nothing can leave the device before the first
+    // hidden state exists (~5 ms at 32 x 10 s), which is what bounds the end-to-end time. Utterances
+    // are independent given the shared max_len, so the result is bit-identical.
     struct Ctx {
-        float* host;
-        size_t per_layer;
-    } ctx{hidden_out, (size_t)batch * T * m->cfg.embed_dim};
+        float* host;        // hidden_out + first utterance of the chunk
+        const float* dev;   // this chunk's [NL+1][Bc][T][D] region of the staging buffer
+        size_t host_layer;  // elements between layers in the host buffer  (batch * T * D)
+        size_t chunk_layer; // elements per layer of this chunk            (Bc * T * D)
+    };
     auto layer_done = [](s3b_model* mm, int l, cudaStream_t s, void* user) -> int {
         Ctx* c = static_cast<Ctx*>(user);
         CUDA_OK(cudaEventRecord(mm->layer_events[l], s));
         CUDA_OK(cudaStreamWaitEvent(mm->copy_stream, mm->layer_events[l], 0));
-        CUDA_OK(cudaMemcpyAsync(c->host + (size_t)l * c->per_layer, mm->stage_out.as<float>() + (size_t)l * c->per_layer,
-                                c->per_layer * 4, cudaMemcpyDeviceToHost, mm->copy_stream));
+        CUDA_OK(cudaMemcpyAsync(c->host + (size_t)l * c->host_layer, c->dev + (size_t)l * c->chunk_layer,
+                                c->chunk_layer * 4, cudaMemcpyDeviceToHost, mm->copy_stream));
         return 0;
     };
-    S3B_OK(forward_impl(m, ptrs.data(), lens, batch, max_len, m->stage_out.as<float>(), st, layer_done, &ctx));
+    int chunks = 1;
+    if (const char* e = getenv("S3B_HOST_CHUNKS")) chunks = atoi(e);
+    if (chunks < 1) chunks = 1;
+    if (chunks > batch) chunks = batch;
+    const size_t frame_elems = (size_t)T * m->cfg.embed_dim;
+    std::vector<Ctx> ctxs(chunks);
+    size_t dev_off = 0;
+    for (int c = 0; c < chunks; ++c) {
+        const int b0 = (int)((int64_t)batch * c / chunks), b1 = (int)((int64_t)batch * (c + 1) / chunks);
+        const int bc = b1 - b0;
+        float* dev = m->stage_out.as<float>() + dev_off;
+        ctxs[c] = Ctx{hidden_out + (size_t)b0 * frame_elems, dev, (size_t)batch * frame_elems, (size_t)bc * frame_elems};
+        S3B_OK(forward_impl(m, ptrs.data() + b0, lens + b0, bc, max_len, dev, st, layer_done, &ctxs[c]));
+        dev_off += (size_t)(m->cfg.num_layers + 1) * bc * frame_elems;
+    }
     CUDA_OK(cudaStreamSynchronize(st));
     CUDA_OK(cudaStreamSynchronize(m->copy_stream));
     return 0;

@@ -6,6 +6,7 @@ Tolerance (north_star): hidden states within 1e-3 relative (fp32); we assert 2e-
 layer (measured ~1e-5) and an elementwise bound of 1e-3 of the layer's absolute maximum.
 The frame padding bookkeeping is asserted bit-exact in tests/test_oracle_cpu.py.
 """
+import os
 import sys
 from pathlib import Path
 
@@ -110,6 +111,22 @@ def test_forward_host_matches_device(s3b_lib):
     dev = torch.stack(expert([w.cuda() for w in wavs])["hidden_states"]).cpu()
     host = expert.forward_host(wavs)
     assert torch.equal(dev, host)
+
+
+@pytest.mark.skipif(os.environ.get("S3B_TEST_EXPERIMENTAL") != "1",
+                    reason="S3B_HOST_CHUNKS (chunked s3b_forward_host) is experimental and off by default")
+def test_forward_host_chunked_matches_device(s3b_lib):
+    """Chunked host forward (chunk c+1's conv stack overlaps chunk c's device->host copies) is bit-identical."""
+    expert = _expert("hubert_base")
+    wavs = _wavs([16000, 9000, 12000, 4000, 16000], seed=6)
+    dev = torch.stack(expert([w.cuda() for w in wavs])["hidden_states"]).cpu()
+    for chunks in ("2", "3", "5", "9"):
+        os.environ["S3B_HOST_CHUNKS"] = chunks
+        try:
+            host = expert.forward_host(wavs)
+        finally:
+            os.environ.pop("S3B_HOST_CHUNKS", None)
+        assert torch.equal(dev, host), chunks
 
 
 def test_short_utterances(s3b_lib):
