@@ -937,8 +937,8 @@ extern "C" int s3b_forward_host(s3b_model* m, const float* const* wavs, const in
         off += (size_t)lens[b];
     }
     // device->host copy of hidden state l overlaps the computation of layer l+1 (second stream).
-    // S3B_HOST_CHUNKS=k (experimental, default 1 = the whole batch at once): the batch is processed as k utterance
-    // chunks so that chunk c+1's conv stack overlaps chunk c's copies — nothing can leave the device before the first
+    // The batch is processed as k utterance chunks (S3B_HOST_CHUNKS=k overrides the default below) so that chunk
+    // c+1's conv stack overlaps chunk c's copies — nothing can leave the device before the first
     // hidden state exists (~5 ms at 32 x 10 s), which is what bounds the end-to-end time. Utterances
     // are independent given the shared max_len, so the result is bit-identical.
     struct Ctx {
@@ -955,7 +955,9 @@ extern "C" int s3b_forward_host(s3b_model* m, const float* const* wavs, const in
                                 c->chunk_layer * 4, cudaMemcpyDeviceToHost, mm->copy_stream));
         return 0;
     };
-    int chunks = 1;
+    // default: two chunks from 16 utterances on (first-output latency ~ half, GEMMs at 16 utterances still run at
+    // ~90 % of their 32-utterance rate); smaller batches are not copy-bound enough to pay for the smaller GEMMs
+    int chunks = batch >= 16 ? 2 : 1;
     if (const char* e = getenv("S3B_HOST_CHUNKS")) chunks = atoi(e);
     if (chunks < 1) chunks = 1;
     if (chunks > batch) chunks = batch;

@@ -113,8 +113,6 @@ def test_forward_host_matches_device(s3b_lib):
     assert torch.equal(dev, host)
 
 
-@pytest.mark.skipif(os.environ.get("S3B_TEST_EXPERIMENTAL") != "1",
-                    reason="S3B_HOST_CHUNKS (chunked s3b_forward_host) is experimental and off by default")
 def test_forward_host_chunked_matches_device(s3b_lib):
     """Chunked host forward (chunk c+1's conv stack overlaps chunk c's device->host copies) is bit-identical."""
     expert = _expert("hubert_base")
