@@ -344,7 +344,8 @@ def run_ours(args):
             "note": "achieved = algorithmic FLOPs (1 MMA per product; the tensor pipe executes 3 bf16 MMAs per product = mma_pipe_tflops) / CUDA-event time per launch, rank 0; traffic = bytes per launch (ncu, profiles/)",
         },
         "kernel_breakdown": breakdown,
-        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+                "host_chunks": int(os.environ.get("S3B_HOST_CHUNKS", 2 if GLOBAL_BATCH // world >= 16 else 1))},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
