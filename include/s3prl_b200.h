@@ -83,6 +83,38 @@ int s3b_forward(s3b_model* m, const float* const* wavs, const int64_t* lens, int
 int s3b_forward_host(s3b_model* m, const float* const* wavs, const int64_t* lens, int32_t batch, int64_t max_len,
                      float* hidden_out);
 
+/* Options of s3b_forward_ex (zero-initialise, set struct_size = sizeof(s3b_forward_opts)).
+ *  lanes            : 0 = default (two utterance micro-batches enqueued alternately on two streams so that one
+ *                     micro-batch's small kernels and tails fill the SMs the other leaves idle; bit-identical to
+ *                     lanes = 1 because utterances are independent given max_len), 1 or 2
+ *  layer_stride     : elements between consecutive hidden states in hidden_out; 0 = batch * T * embed_dim. A caller
+ *                     that runs a sub-batch into its slice of a larger [NL+1][Btotal][T][D] buffer passes Btotal*T*D.
+ *  ffn_out          : optional DEVICE [num_layers][batch][T][embed_dim]: fc2 output (+bias) of every layer BEFORE
+ *                     the residual add = layer_results[i][2] of the reference (wav2vec2/expert.py:87-93,
+ *                     feature_selection "fairseq_layers_before_residual"); ffn_layer_stride like layer_stride
+ *  last_residual    : optional DEVICE [batch][T][embed_dim], layer_norm_first models only: output of the last layer
+ *                     before encoder.layer_norm = layer_results[-1][0] ("fairseq_layers", wav2vec2/expert.py:81-86) */
+typedef struct s3b_forward_opts {
+    int32_t struct_size;
+    int32_t lanes;
+    int64_t layer_stride;
+    float* ffn_out;
+    int64_t ffn_layer_stride;
+    float* last_residual;
+    int64_t reserved[4];
+} s3b_forward_opts;
+int s3b_forward_ex(s3b_model* m, const float* const* wavs, const int64_t* lens, int32_t batch, int64_t max_len,
+                   float* hidden_out, void* stream, const s3b_forward_opts* opts);
+/* s3b_forward_host that also leaves the hidden states in a caller-owned DEVICE buffer [NL+1][batch][T][D]
+ * (hidden_out_dev may be NULL = internal staging), so that a device-side consumer (Featurizer, all-gather) can run
+ * without re-uploading them. */
+int s3b_forward_host_ex(s3b_model* m, const float* const* wavs, const int64_t* lens, int32_t batch, int64_t max_len,
+                        float* hidden_out, float* hidden_out_dev);
+
+/* WavLM relative-position bucket of rel[i] = key - query, bidirectional (integer rule, bit-exact with
+ * MultiheadAttention._relative_positions_bucket, s3prl/upstream/wavlm/modules.py:418-448). Host arithmetic. */
+int s3b_wavlm_buckets(int32_t num_buckets, int32_t max_distance, const int32_t* rel, int32_t n, int32_t* out);
+
 /* Accounting --------------------------------------------------------------------------------------
  * Kernel categories: 0 = tcgen05 GEMM, 1 = tcgen05 attention, 2 = conv-0 (+GroupNorm/LayerNorm+GELU),
  * 3 = LayerNorm kernels, 4 = misc (waveform packing, WavLM gate). With profiling enabled every launch of

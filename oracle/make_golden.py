@@ -44,6 +44,15 @@ CASES = {
 }
 
 
+# BASELINE.json sizes (C3 = wav2vec2_large 20 s -> T = 999, C4 = wavlm_base_plus 10 s -> T = 499) on a batch
+# the CPU reference can afford: fixture name -> (architecture, cases, channel stride, time stride of the sub-sample)
+FULL_SIZE = {
+    "c3_wav2vec2_large_960": ("wav2vec2_large_960", [[320000, 320000]], 13, 8),
+    "c3_wav2vec2_large_ll60k": ("wav2vec2_large_ll60k", [[320000, 271828]], 13, 8),
+    "c4_wavlm_base_plus": ("wavlm_base_plus", [[160000, 160000], [160000, 100003]], 7, 4),
+}
+
+
 def seeded_wavs(lens, seed):
     g = torch.Generator().manual_seed(seed)
     return [torch.randn(n, generator=g) for n in lens]
@@ -126,11 +135,14 @@ def reference_expert(name: str, sd):
     return expert
 
 
-def make_model_fixture(name: str):
-    lens_cases, cstride = CASES[name]
+def make_model_fixture(name: str, fixture: str = None):
+    if fixture is None:
+        (lens_cases, cstride), tstride, fixture = CASES[name], 1, name
+    else:
+        name, lens_cases, cstride, tstride = FULL_SIZE[fixture]
     sd = fabricate_state_dict(ARCHS[name], seed=0)
     expert = reference_expert(name, sd)
-    out = {"arch": name, "weight_seed": 0, "channel_stride": cstride, "cases": []}
+    out = {"arch": name, "weight_seed": 0, "channel_stride": cstride, "time_stride": tstride, "cases": []}
     for ci, lens in enumerate(lens_cases):
         wavs = seeded_wavs(lens, seed=100 + ci)
         with torch.no_grad():
@@ -142,13 +154,14 @@ def make_model_fixture(name: str):
                 "wav_seed": 100 + ci,
                 "shape": tuple(hs[0].shape),
                 "num_hidden": len(hs),
-                "sub": torch.stack([h[:, :, ::cstride].contiguous() for h in hs]),
+                # time sub-sample anchored at the LAST frame so that the end of the sequence is always covered
+                "sub": torch.stack([h[:, (h.shape[1] - 1) % tstride :: tstride, ::cstride].contiguous() for h in hs]),
                 "norms": torch.tensor([h.double().norm().item() for h in hs]),
                 "abs_max": torch.tensor([h.abs().max().item() for h in hs]),
             }
         )
-        print(f"{name} case {ci}: lens={lens} -> {len(hs)} x {tuple(hs[0].shape)}")
-    torch.save(out, GOLDEN / f"{name}.pt")
+        print(f"{fixture} case {ci}: lens={lens} -> {len(hs)} x {tuple(hs[0].shape)}", flush=True)
+    torch.save(out, GOLDEN / f"{fixture}.pt")
 
 
 def make_integer_fixture():
@@ -159,13 +172,23 @@ def make_integer_fixture():
     from s3prl.upstream.wavlm.modules import MultiheadAttention as WavLMAttention
 
     g = torch.Generator().manual_seed(7)
-    batches = []
+    batches, short_batches = [], []
     w2v = Wav2Vec2Model(Wav2Vec2Config(encoder_layers=1, quantize_targets=False))
-    for _ in range(60):
-        B = int(torch.randint(1, 7, (1,), generator=g))
-        lens = torch.randint(400, 170000, (B,), generator=g).tolist()
-        if torch.rand(1, generator=g).item() < 0.3:
-            lens = [max(lens)] * B  # no padding at all
+    # 60 random batches, then batches holding utterances SHORTER than the 400-sample receptive field (the wav2vec2
+    # rule's unclamped floor arithmetic goes to 0 / negative there and the mask index wraps around)
+    short = [[16000, 50], [16000, 5], [8000, 399, 55, 56, 57, 1], [16000, 400, 401, 719, 720, 721], [4000, 10, 9, 14, 15, 16]]
+    g2 = torch.Generator().manual_seed(11)
+    for _ in range(12):
+        short.append([int(torch.randint(2000, 40000, (1,), generator=g2))] + torch.randint(1, 400, (4,), generator=g2).tolist())
+    for it in range(60 + len(short)):
+        if it >= 60:
+            lens = short[it - 60]
+            B = len(lens)
+        else:
+            B = int(torch.randint(1, 7, (1,), generator=g))
+            lens = torch.randint(400, 170000, (B,), generator=g).tolist()
+            if torch.rand(1, generator=g).item() < 0.3:
+                lens = [max(lens)] * B  # no padding at all
         Lmax = max(lens)
         pad = ~torch.lt(torch.arange(Lmax).unsqueeze(0), torch.tensor(lens).unsqueeze(1))
         n = Lmax
@@ -184,7 +207,7 @@ def make_integer_fixture():
             w2v_valid = [int((~r).sum()) for r in w2v_mask]
         else:
             w2v_valid = [T] * B
-        batches.append(
+        (batches if it < 60 else short_batches).append(
             {
                 "lens": lens,
                 "T": T,
@@ -198,8 +221,9 @@ def make_integer_fixture():
     att = WavLMAttention(768, 12, has_relative_attention_bias=True, num_buckets=320, max_distance=800)
     rel = torch.arange(-2100, 2101, dtype=torch.long)
     buckets = att._relative_positions_bucket(rel.unsqueeze(0), bidirectional=True)[0]
-    torch.save({"batches": batches, "wavlm_rel": rel, "wavlm_bucket": buckets}, GOLDEN / "integer_rules.pt")
-    print(f"integer rules: {len(batches)} batches, {len(rel)} relative positions")
+    torch.save({"batches": batches, "short_batches": short_batches, "wavlm_rel": rel, "wavlm_bucket": buckets},
+               GOLDEN / "integer_rules.pt")
+    print(f"integer rules: {len(batches)} + {len(short_batches)} batches, {len(rel)} relative positions")
 
 
 def make_fbank_fixture():
@@ -254,6 +278,9 @@ def main():
     for name in CASES:
         if args.only in (None, name):
             make_model_fixture(name)
+    for fixture in FULL_SIZE:
+        if args.only in (None, fixture, "full_size"):
+            make_model_fixture(None, fixture)
 
 
 if __name__ == "__main__":

@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
         const float* brow = nullptr;
         if (kBias) {
             gate = (p.gate == nullptr) ? 1.0f : (row_ok ? p.gate[((size_t)b * p.H + h) * p.T + q_row] : 0.f);
-            brow = p.bias_table + (size_t)h * (2 * p.T - 1) + (p.T - 1 - (row_ok ? q_row : 0));  // index by key k
+            brow = p.bias_table + (size_t)h * p.bias_stride + (p.bias_center - (row_ok ? q_row : 0));  // index by key k
         }
         float m_run = -INFINITY;  // running row max (log2 domain)
         float l_run = 0.f;        // this thread's share of the row sum

@@ -47,6 +47,7 @@ struct GemmParams {
     float* out_f32;
     __nv_bfloat16* out_hi;
     __nv_bfloat16* out_lo;
+    float* out_pre;  // optional: v BEFORE the residual add (fc2 output, "fairseq_layers_before_residual"), same layout
 
     // ---- epilogue, QKV scatter mode (qkv_mode != 0): columns [0,D) -> q*scale, [D,2D) -> k, [2D,3D) -> v
     // q,k: [B][H][T][64] split bf16 ; v transposed: [B][H][64][Tp] split bf16. Flat row m = b*T + t.

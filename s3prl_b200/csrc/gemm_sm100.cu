@@ -121,6 +121,11 @@ __device__ __forceinline__ void epilogue_cols(const GemmParams& p, const uint32_
     }
 
     const size_t off = m * (size_t)p.ldo + col;
+    if (p.out_pre != nullptr) {
+        float4* d4 = reinterpret_cast<float4*>(p.out_pre + off);
+#pragma unroll
+        for (int j = 0; j < NC / 4; ++j) d4[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+    }
     if (p.residual != nullptr) {
 #pragma unroll
         for (int j = 0; j < NC / 4; ++j) {
@@ -228,9 +233,10 @@ __device__ __forceinline__ void epi_chunk_coalesced(const GemmParams& p, const E
             *reinterpret_cast<uint2*>((which == 0 ? p.q_lo : p.k_lo) + o) = make_uint2(l0, l1);
             continue;
         }
+        const size_t o = er.off[it] + col + 4 * cs;
+        if (p.out_pre != nullptr) *reinterpret_cast<float4*>(p.out_pre + o) = x;
         if (p.residual != nullptr) x.x += res[it].x, x.y += res[it].y, x.z += res[it].z, x.w += res[it].w;
         if ((er.mask_bits >> it) & 1u) x = make_float4(0.f, 0.f, 0.f, 0.f);
-        const size_t o = er.off[it] + col + 4 * cs;
         if (p.out_f32 != nullptr) *reinterpret_cast<float4*>(p.out_f32 + o) = x;
         if (p.out_hi != nullptr) {
             uint32_t h0, l0, h1, l1;

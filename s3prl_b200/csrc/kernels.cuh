@@ -41,8 +41,9 @@ struct AttnParams {
     CUtensorMap vt_hi, vt_lo;  // [B*H][64][Tp] (dim0 = T valid keys) box {64, 64, 1}
     int B, H, T, D;
     const int* kv_len;          // [B] valid (un-padded) key count, >= 1
-    // optional WavLM gated relative position bias: S[q][k] += gate[b][h][q] * table[h][k - q + T - 1]
-    const float* bias_table;    // [H][2T-1] or null
+    // optional WavLM gated relative position bias: S[q][k] += gate[b][h][q] * table[h][k - q + bias_center]
+    const float* bias_table;    // [H][bias_stride], entry (h, k - q + bias_center); or null
+    int bias_stride, bias_center;
     const float* gate;          // [B][H][T] or null
     __nv_bfloat16 *ctx_hi, *ctx_lo;  // [B*T][D] split bf16 (A operand of out_proj)
     // optional timeline (debug): clock64 stamps of CTA `trace_block`, [2 roles][16 blocks][8 slots]

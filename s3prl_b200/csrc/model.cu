@@ -63,6 +63,9 @@ struct HostTensor {
     size_t numel() const { return data.size(); }
 };
 
+// bumped on every (re)allocation: cached launch plans hold raw device pointers and are rebuilt when it moves
+static uint64_t g_alloc_generation = 1;
+
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
@@ -71,6 +74,7 @@ struct DevBuf {
         if (n <= bytes) return 0;
         if (p) cudaFree(p);
         p = nullptr, bytes = 0;
+        ++g_alloc_generation;
         cudaError_t e = cudaMalloc(&p, n);
         if (e != cudaSuccess) return fail("cudaMalloc(%zu) failed: %s", n, cudaGetErrorString(e));
         // zero once so that never-written padding is finite (0 * garbage must not be NaN)
@@ -138,6 +142,25 @@ struct Profiler {
     }
 };
 
+// Per-lane working set. A forward call runs the batch as one or two utterance micro-batches ("lanes"): lane 0 on
+// the caller's stream, lane 1 on an internal stream, every kernel enqueue alternating between the two so that one
+// lane's tails / small kernels fill the SMs the other leaves idle. Utterances are independent given the shared
+// max_len, so the result is bit-identical to the single-lane run (tests/test_properties_gpu.py).
+struct Plan;
+struct Workspace {
+    // bookkeeping block (one pinned host mirror, one async H2D copy per call): wav ptrs | lens | kv_len | row mask
+    DevBuf book;
+    void* book_host = nullptr;
+    size_t book_host_bytes = 0;
+    cudaEvent_t book_copied = nullptr;  // the previous call's H2D copy has been consumed: the mirror may be rewritten
+    DevBuf wav_stats, wav_pad, c0_part, c0_ss, conv_f32, tmp_f32, x_f32, x1_f32, gate, pos_z;
+    SplitBuf act[kNumConv], ln512_s, x_s, xs_s, q_s, k_s, vt_s, ctx_s, x1_s, h_s;
+    cudaStream_t stream = nullptr;  // lane stream (lane 1; lane 0 runs on the caller's stream)
+    cudaEvent_t done = nullptr;
+    std::vector<Plan*> plans;  // small LRU of cached tensor maps / launch descriptors keyed by (B, Lmax)
+    void release();
+};
+
 struct s3b_model {
     s3b_config cfg;
     std::map<std::string, HostTensor> host;
@@ -146,6 +169,7 @@ struct s3b_model {
     Profiler prof;
     long long launches_total = 0;  // kernels launched by this model since creation
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+    cudaEvent_t fork_event = nullptr;
     std::vector<cudaEvent_t> layer_events;
 
     // weights
@@ -154,19 +178,13 @@ struct s3b_model {
     DevBuf conv_b[kNumConv], conv_ln_g[kNumConv], conv_ln_b[kNumConv];
     DevBuf ln512_g, ln512_b, proj_b, pos_b, enc_ln_g, enc_ln_b;
     SplitBuf proj_w, pos_w, pos_w4;  // pos_w4: four-taps-per-k-block layout (posconv4_params)
-    DevBuf pos_z;                    // [B][T+3][4*D] fp32 scratch of the four-tap pos_conv GEMM
     DevBuf rel_table_src;  // WavLM relative_attention_bias.weight [num_buckets][H]
+    DevBuf rel_table;      // [H][2*rel_table_T - 1] gathered table (x log2 e), built at finalize for rel_table_T frames
+    int rel_table_T = 0;
     std::vector<LayerW> layers;
 
-    // workspace (grown on demand, reused across calls)
-    DevBuf wav_ptrs, lens_dev, kvlen_dev, rowmask_dev, wav_stats, wav_pad;
-    DevBuf c0_part, c0_ss, conv_f32, tmp_f32, x_f32, x1_f32, gate, rel_table;
-    SplitBuf act[kNumConv], ln512_s, x_s, xs_s, q_s, k_s, vt_s, ctx_s, x1_s, h_s;
+    Workspace ws[2];
     DevBuf stage_wav, stage_out;  // s3b_forward_host staging
-    std::vector<long long> lens_host;
-    std::vector<int> kv_host;
-    std::vector<uint8_t> mask_host;
-    int rel_table_T = -1;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -219,7 +237,7 @@ static int64_t num_frames(int64_t L) {
 // ------------------------------------------------------------------------------------------------
 // C ABI: library
 // ------------------------------------------------------------------------------------------------
-extern "C" int s3b_version(void) { return 100; }
+extern "C" int s3b_version(void) { return 200; }
 extern "C" const char* s3b_last_error(void) { return g_last_error.c_str(); }
 extern "C" int s3b_device_count(void) {
     int n = 0;
@@ -264,17 +282,12 @@ extern "C" int s3b_model_set_tensor(s3b_model* m, const char* name, const float*
 extern "C" void s3b_model_destroy(s3b_model* m) {
     if (!m) return;
     DevBuf* bufs[] = {&m->conv0_w, &m->conv0_b, &m->norm0_g, &m->norm0_b, &m->ln512_g, &m->ln512_b, &m->proj_b,
-                      &m->pos_b, &m->enc_ln_g, &m->enc_ln_b, &m->rel_table_src, &m->wav_ptrs, &m->lens_dev,
-                      &m->kvlen_dev, &m->rowmask_dev, &m->wav_stats, &m->wav_pad, &m->c0_part, &m->c0_ss,
-                      &m->conv_f32, &m->tmp_f32, &m->x_f32, &m->x1_f32, &m->gate, &m->rel_table, &m->stage_wav,
-                      &m->stage_out, &m->pos_z};
+                      &m->pos_b, &m->enc_ln_g, &m->enc_ln_b, &m->rel_table_src, &m->rel_table, &m->stage_wav,
+                      &m->stage_out};
     for (DevBuf* b : bufs) b->release();
-    for (int i = 0; i < kNumConv; ++i) {
+    for (int i = 0; i < kNumConv; ++i)
         m->conv_w[i].release(), m->conv_b[i].release(), m->conv_ln_g[i].release(), m->conv_ln_b[i].release();
-        m->act[i].release();
-    }
-    SplitBuf* sb[] = {&m->proj_w, &m->pos_w, &m->pos_w4, &m->ln512_s, &m->x_s, &m->xs_s, &m->q_s, &m->k_s, &m->vt_s, &m->ctx_s,
-                      &m->x1_s, &m->h_s};
+    SplitBuf* sb[] = {&m->proj_w, &m->pos_w, &m->pos_w4};
     for (SplitBuf* b : sb) b->release();
     for (LayerW& l : m->layers) {
         l.qkv.release(), l.out.release(), l.fc1.release(), l.fc2.release();
@@ -282,7 +295,25 @@ extern "C" void s3b_model_destroy(s3b_model* m) {
                         &l.grep_w, &l.grep_b, &l.grep_a};
         for (DevBuf* b : lb) b->release();
     }
+    for (Workspace& w : m->ws) w.release();
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+    if (m->compute_stream) cudaStreamDestroy(m->compute_stream);
+    if (m->fork_event) cudaEventDestroy(m->fork_event);
+    for (cudaEvent_t e : m->layer_events) cudaEventDestroy(e);
     delete m;
+}
+
+// WavLM: table[h][r] = log2(e) * emb[bucket(r - (Tmax - 1))][h], r in [0, 2 Tmax - 1). Built once for Tmax frames
+// (the ungated bias is shared by all layers and all calls, WavLM.py:622-632); the attention kernel indexes it with
+// the centre Tmax - 1, so a forward never allocates or synchronises for it (it used to rebuild per distinct T).
+static int build_rel_table(s3b_model* m, int Tmax) {
+    const s3b_config& c = m->cfg;
+    S3B_OK(m->rel_table.ensure((size_t)c.num_heads * (2 * (size_t)Tmax - 1) * 4));
+    CUDA_OK(launch_wavlm_rel_table(m->rel_table_src.as<float>(), c.num_buckets, c.max_distance, c.num_heads, Tmax,
+                                   m->rel_table.as<float>(), 0));
+    CUDA_OK(cudaDeviceSynchronize());
+    m->rel_table_T = Tmax;
+    return 0;
 }
 
 extern "C" int s3b_model_finalize(s3b_model* m) {
@@ -421,6 +452,7 @@ extern "C" int s3b_model_finalize(s3b_model* m) {
     if (c.relative_position) {
         S3B_OK(need(m, "encoder.layers.0.self_attn.relative_attention_bias.weight", {c.num_buckets, c.num_heads}, &t));
         S3B_OK(upload_f32(m->rel_table_src, t->data.data(), t->numel()));
+        S3B_OK(build_rel_table(m, 4096));  // utterances up to 82 s; rebuilt (synchronously) for longer batches
     }
     m->host.clear();
     m->finalized = true;
@@ -448,9 +480,21 @@ extern "C" int s3b_valid_frames(const s3b_model* m, const int64_t* lens, int32_t
     for (int b = 0; b < batch; ++b) {
         int64_t v;
         if (m->cfg.family == 1) {
-            // wav2vec2: conv-length rule, only when the batch has any padding (wav2vec2_model.py:2652-2671)
-            v = any_pad ? num_frames(lens[b]) : T;
-            if (v < 1) v = T;  // output_lengths - 1 == -1 indexes the last frame: every frame stays valid
+            // wav2vec2: conv-length rule, only when the batch has any padding (wav2vec2_model.py:2652-2671). The
+            // reference evaluates floor((n - k) / s + 1) in fp32 WITHOUT clamping, so an utterance shorter than the
+            // receptive field yields 0 or a negative length and `mask[b, length - 1] = 1` wraps around like any
+            // negative Python index: valid = ((length - 1) mod T) + 1.
+            if (!any_pad) {
+                v = T;
+            } else {
+                float n = (float)lens[b];
+                for (int i = 0; i < kNumConv; ++i) n = floorf((n - (float)kConvK[i]) / (float)kConvS[i] + 1.0f);
+                int64_t idx = (int64_t)n - 1;
+                if (idx < -T) return fail("lens[%d]=%lld: the reference's mask index %lld is out of range for T=%lld",
+                                          b, (long long)lens[b], (long long)idx, (long long)T);
+                if (idx < 0) idx += T;
+                v = idx + 1;
+            }
         } else {
             // HuBERT / WavLM: frame t is padding iff all samples of chunk t are padding, chunk = Lmax // T
             const int64_t chunk = max_len / T;
@@ -458,6 +502,17 @@ extern "C" int s3b_valid_frames(const s3b_model* m, const int64_t* lens, int32_t
         }
         valid[b] = (int32_t)(v > T ? T : v);
     }
+    return 0;
+}
+
+// WavLM relative-position buckets (modules.py:418-448), exported so that the product's integer rule can be pinned
+// against the reference-generated table (tests/test_oracle_cpu.py); pure host arithmetic, no GPU needed.
+extern "C" int s3b_wavlm_buckets(int32_t num_buckets, int32_t max_distance, const int32_t* rel, int32_t n,
+                                 int32_t* out) {
+    if (!rel || !out || n < 0) return fail("null argument");
+    if (num_buckets < 4 || num_buckets % 4 != 0 || max_distance <= num_buckets / 4)
+        return fail("num_buckets must be a positive multiple of 4 and max_distance > num_buckets / 4");
+    for (int i = 0; i < n; ++i) out[i] = wavlm_rel_bucket(rel[i], num_buckets, max_distance);
     return 0;
 }
 
@@ -648,18 +703,84 @@ static inline void prof_end(s3b_model* m, cudaStream_t st, int cat, int nkernels
 #define KMISC(expr) KLAUNCH(CAT_MISC, 1, 0.0, expr)
 
 // ------------------------------------------------------------------------------------------------
-// forward
+// cached launch plan: every tensor map / GEMM descriptor of one forward at a given (B, Lmax)
+// ------------------------------------------------------------------------------------------------
+// Encoding the ~22 CUtensorMaps of a layer costs ~300 driver calls per forward; they only depend on the workspace
+// addresses, the weights and (B, T), so they are built once per shape and reused (ragged training batches change
+// Lmax every step and rebuild; fixed-shape serving never does). Pointers into the caller's hidden_out buffer are
+// plain epilogue fields and are patched per call.
+struct LayerPlan {
+    GemmParams qkv, out, fc1, fc2;
+    AttnParams attn;
+};
+struct Plan {
+    int B = 0;
+    int64_t Lmax = 0;
+    uint64_t gen = 0;
+    GemmParams conv[kNumConv];
+    GemmParams proj, pos;
+    std::vector<LayerPlan> layers;
+};
+
+void Workspace::release() {
+    DevBuf* bufs[] = {&book, &wav_stats, &wav_pad, &c0_part, &c0_ss, &conv_f32, &tmp_f32, &x_f32, &x1_f32, &gate, &pos_z};
+    for (DevBuf* b : bufs) b->release();
+    for (int i = 0; i < kNumConv; ++i) act[i].release();
+    SplitBuf* sb[] = {&ln512_s, &x_s, &xs_s, &q_s, &k_s, &vt_s, &ctx_s, &x1_s, &h_s};
+    for (SplitBuf* b : sb) b->release();
+    if (book_host) cudaFreeHost(book_host);
+    book_host = nullptr, book_host_bytes = 0;
+    if (book_copied) cudaEventDestroy(book_copied);
+    if (done) cudaEventDestroy(done);
+    if (stream) cudaStreamDestroy(stream);
+    book_copied = nullptr, done = nullptr, stream = nullptr;
+    for (Plan* p : plans) delete p;
+    plans.clear();
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward (one lane = one utterance micro-batch) as a sequence of stages
 // ------------------------------------------------------------------------------------------------
 // layer_done: optional callback fired (host side) right after hidden state `l` has been enqueued completely
 typedef int (*LayerDoneFn)(s3b_model*, int l, cudaStream_t st, void* user);
 
-static int forward_impl(s3b_model* m, const float* const* wavs_dev, const int64_t* lens, int B, int64_t Lmax,
-                        float* hidden_out, cudaStream_t st, LayerDoneFn layer_done = nullptr,
-                        void* user = nullptr) {
-    const s3b_config& c = m->cfg;
-    const int D = c.embed_dim, F = c.ffn_dim, H = c.num_heads, NL = c.num_layers, C = kConvDim;
-    if (B < 1) return fail("empty batch");
+struct Fwd {
+    // inputs
+    s3b_model* m = nullptr;
+    Workspace* w = nullptr;
+    cudaStream_t st = nullptr;
+    const float* const* wavs = nullptr;  // host array of device pointers (this lane's utterances)
+    const int64_t* lens = nullptr;
+    int B = 0;
+    int64_t Lmax = 0;
+    float* hidden = nullptr;   // this lane's first utterance inside hidden state 0
+    size_t layer_stride = 0;   // elements between consecutive hidden states
+    float* ffn_out = nullptr;  // optional: fc2 output (+bias) before the residual add, [NL][...] like hidden
+    size_t ffn_stride = 0;
+    float* last_res = nullptr;  // optional (pre-LN models): un-normalised output of the last layer
+    LayerDoneFn layer_done = nullptr;
+    void* user = nullptr;
+    // derived
     int64_t L[kNumConv];
+    int T = 0, Tp = 0;
+    int64_t M = 0;
+    Plan* plan = nullptr;
+    const float** d_wavs = nullptr;
+    long long* d_lens = nullptr;
+    int* d_kv = nullptr;
+    uint8_t* d_mask = nullptr;
+
+    int num_stages() const { return 9 + 5 * m->cfg.num_layers; }
+    int prepare();
+    int build_plan(Plan& pl);
+    int stage(int s);
+    float* hs(int l) const { return hidden + (size_t)l * layer_stride; }
+};
+
+int Fwd::prepare() {
+    const s3b_config& c = m->cfg;
+    const int D = c.embed_dim, F = c.ffn_dim, H = c.num_heads, C = kConvDim;
+    if (B < 1) return fail("empty batch");
     {
         int64_t cur = Lmax;
         for (int i = 0; i < kNumConv; ++i) cur = L[i] = conv_out_len(cur, i);
@@ -667,237 +788,409 @@ static int forward_impl(s3b_model* m, const float* const* wavs_dev, const int64_
     const int64_t T64 = L[kNumConv - 1];
     if (T64 < 1) return fail("max_len %lld too short: the conv stack yields no frame", (long long)Lmax);
     if ((int64_t)B * L[0] > 2000000000LL) return fail("batch too large for 32-bit tile indexing");
-    const int T = (int)T64;
-    const int64_t M = (int64_t)B * T;
-    const int Tp = (T + 7) & ~7;
-    const double attn_flops = 4.0 * (double)T * T * D * B;
-    const double conv0_flops = 2.0 * kConvK[0] * C * (double)B * L[0];
+    T = (int)T64;
+    M = (int64_t)B * T;
+    Tp = (T + 7) & ~7;
+    if (layer_stride == 0) layer_stride = (size_t)M * D;
+    if (ffn_out != nullptr && ffn_stride == 0) ffn_stride = (size_t)M * D;
+    if (c.relative_position && T > m->rel_table_T) S3B_OK(build_rel_table(m, 2 * T));
 
-    // ---- host-side integer bookkeeping -> device -------------------------------------------------------
-    m->kv_host.resize(B);
-    S3B_OK(s3b_valid_frames(m, lens, B, Lmax, m->kv_host.data()));
-    m->lens_host.assign(lens, lens + B);
-    m->mask_host.assign((size_t)M, 0);
-    for (int b = 0; b < B; ++b)
-        for (int t = m->kv_host[b]; t < T; ++t) m->mask_host[(size_t)b * T + t] = 1;
-    S3B_OK(m->wav_ptrs.ensure(B * sizeof(void*)));
-    S3B_OK(m->lens_dev.ensure(B * sizeof(long long)));
-    S3B_OK(m->kvlen_dev.ensure(B * sizeof(int)));
-    S3B_OK(m->rowmask_dev.ensure((size_t)M));
-    CUDA_OK(cudaMemcpyAsync(m->wav_ptrs.p, wavs_dev, B * sizeof(void*), cudaMemcpyHostToDevice, st));
-    CUDA_OK(cudaMemcpyAsync(m->lens_dev.p, m->lens_host.data(), B * sizeof(long long), cudaMemcpyHostToDevice, st));
-    CUDA_OK(cudaMemcpyAsync(m->kvlen_dev.p, m->kv_host.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
-    CUDA_OK(cudaMemcpyAsync(m->rowmask_dev.p, m->mask_host.data(), (size_t)M, cudaMemcpyHostToDevice, st));
-
-    // ---- workspace ----------------------------------------------------------------------------------
-    S3B_OK(m->wav_pad.ensure((size_t)B * Lmax * 4));
-    S3B_OK(m->wav_stats.ensure((size_t)B * 2 * 4));
-    S3B_OK(m->c0_part.ensure(conv0_ws_part_floats(B, (int)L[0]) * 4));
-    S3B_OK(m->c0_ss.ensure((size_t)2 * B * C * 4));
-    for (int i = 0; i < kNumConv - 1; ++i) S3B_OK(m->act[i].ensure((size_t)B * L[i] * C));
-    S3B_OK(m->conv_f32.ensure((size_t)B * (c.extractor_layer_norm ? L[1] : L[6]) * C * 4));
-    S3B_OK(m->ln512_s.ensure((size_t)M * C));
-    S3B_OK(m->tmp_f32.ensure((size_t)M * D * 4));
-    S3B_OK(m->x_f32.ensure((size_t)M * D * 4));
-    S3B_OK(m->x1_f32.ensure((size_t)M * D * 4));
-    S3B_OK(m->x_s.ensure((size_t)M * D));
-    S3B_OK(m->xs_s.ensure((size_t)M * D));
-    S3B_OK(m->x1_s.ensure((size_t)M * D));
-    S3B_OK(m->ctx_s.ensure((size_t)M * D));
-    S3B_OK(m->q_s.ensure((size_t)M * D));
-    S3B_OK(m->k_s.ensure((size_t)M * D));
-    S3B_OK(m->vt_s.ensure((size_t)B * H * 64 * Tp));
-    S3B_OK(m->h_s.ensure((size_t)M * F));
-
-    // ---- waveform packing (+ normalisation) ------------------------------------------------------------
-    KMISC(launch_wav_pack(m->wav_ptrs.as<const float*>(), m->lens_dev.as<long long>(), B, Lmax, c.normalize_wav,
-                            m->wav_stats.as<float>(), m->wav_pad.as<float>(), st));
-
-    // ---- conv 0 + norm + GELU -> act[0] (bf16 hi/lo, channels-last) -----------------------------------------
-    if (c.extractor_layer_norm) {
-        KCONV0(1, launch_conv0_layernorm(m->wav_pad.as<float>(), B, Lmax, (int)L[0], m->conv0_w.as<float>(),
-                                       c.conv_bias ? m->conv0_b.as<float>() : nullptr, m->norm0_g.as<float>(),
-                                       m->norm0_b.as<float>(), m->act[0].h(), m->act[0].l(), st));
-    } else {
-        if (c.conv_bias) return fail("conv_bias with extractor_mode=default is not supported");
-        KCONV0(3, launch_conv0_groupnorm(m->wav_pad.as<float>(), B, Lmax, (int)L[0], m->conv0_w.as<float>(),
-                                       m->norm0_g.as<float>(), m->norm0_b.as<float>(), m->c0_part.as<float>(),
-                                       m->c0_ss.as<float>(), m->act[0].h(), m->act[0].l(), st));
+    // ---- bookkeeping block: pinned host mirror -> one async copy ---------------------------------------------
+    const size_t off_lens = (size_t)B * sizeof(void*);
+    const size_t off_kv = off_lens + (size_t)B * sizeof(long long);
+    const size_t off_mask = (off_kv + (size_t)B * sizeof(int) + 15) & ~(size_t)15;
+    const size_t book_bytes = off_mask + (size_t)M;
+    S3B_OK(w->book.ensure(book_bytes));
+    if (w->book_host_bytes < book_bytes) {
+        if (w->book_copied) CUDA_OK(cudaEventSynchronize(w->book_copied));
+        if (w->book_host) cudaFreeHost(w->book_host);
+        w->book_host = nullptr, w->book_host_bytes = 0;
+        const size_t cap = book_bytes * 2 + 4096;
+        CUDA_OK(cudaHostAlloc(&w->book_host, cap, cudaHostAllocDefault));
+        w->book_host_bytes = cap;
     }
+    if (w->book_copied == nullptr) CUDA_OK(cudaEventCreateWithFlags(&w->book_copied, cudaEventDisableTiming));
+    else CUDA_OK(cudaEventSynchronize(w->book_copied));  // normally long complete
+    {
+        char* hb = static_cast<char*>(w->book_host);
+        memcpy(hb, wavs, (size_t)B * sizeof(void*));
+        long long* hl = reinterpret_cast<long long*>(hb + off_lens);
+        int* hk = reinterpret_cast<int*>(hb + off_kv);
+        uint8_t* hm = reinterpret_cast<uint8_t*>(hb + off_mask);
+        S3B_OK(s3b_valid_frames(m, lens, B, Lmax, hk));
+        for (int b = 0; b < B; ++b) hl[b] = (long long)lens[b];
+        memset(hm, 0, (size_t)M);
+        for (int b = 0; b < B; ++b)
+            for (int t = hk[b]; t < T; ++t) hm[(size_t)b * T + t] = 1;
+    }
+    char* db = w->book.as<char>();
+    d_wavs = reinterpret_cast<const float**>(db);
+    d_lens = reinterpret_cast<long long*>(db + off_lens);
+    d_kv = reinterpret_cast<int*>(db + off_kv);
+    d_mask = reinterpret_cast<uint8_t*>(db + off_mask);
 
-    // ---- conv 1..6 as implicit GEMM -------------------------------------------------------------------
-    GemmParams p;
+    // ---- workspace ------------------------------------------------------------------------------------------
+    S3B_OK(w->wav_pad.ensure((size_t)B * Lmax * 4));
+    S3B_OK(w->wav_stats.ensure((size_t)B * 2 * 4));
+    S3B_OK(w->c0_part.ensure(conv0_ws_part_floats(B, (int)L[0]) * 4));
+    S3B_OK(w->c0_ss.ensure((size_t)2 * B * C * 4));
+    for (int i = 0; i < kNumConv - 1; ++i) S3B_OK(w->act[i].ensure((size_t)B * L[i] * C));
+    S3B_OK(w->conv_f32.ensure((size_t)B * (c.extractor_layer_norm ? L[1] : L[6]) * C * 4));
+    S3B_OK(w->ln512_s.ensure((size_t)M * C));
+    S3B_OK(w->tmp_f32.ensure((size_t)M * D * 4));
+    S3B_OK(w->x_f32.ensure((size_t)M * D * 4));
+    S3B_OK(w->x1_f32.ensure((size_t)M * D * 4));
+    S3B_OK(w->x_s.ensure((size_t)M * D));
+    S3B_OK(w->xs_s.ensure((size_t)M * D));
+    S3B_OK(w->x1_s.ensure((size_t)M * D));
+    S3B_OK(w->ctx_s.ensure((size_t)M * D));
+    S3B_OK(w->q_s.ensure((size_t)M * D));
+    S3B_OK(w->k_s.ensure((size_t)M * D));
+    S3B_OK(w->vt_s.ensure((size_t)B * H * 64 * Tp));
+    S3B_OK(w->h_s.ensure((size_t)M * F));
+    if (posconv4_ok(c)) S3B_OK(w->pos_z.ensure((size_t)B * (T + 3) * 4 * D * sizeof(float)));
+    if (c.relative_position) S3B_OK(w->gate.ensure((size_t)B * H * T * 4));
+
+    // ---- launch plan (cached per (B, Lmax) while no buffer has been reallocated) --------------------------------
+    plan = nullptr;
+    for (size_t i = 0; i < w->plans.size(); ++i) {
+        Plan* pl = w->plans[i];
+        if (pl->B == B && pl->Lmax == Lmax && pl->gen == g_alloc_generation) {
+            plan = pl;
+            w->plans.erase(w->plans.begin() + i);
+            w->plans.insert(w->plans.begin(), pl);
+            break;
+        }
+    }
+    if (plan == nullptr) {
+        Plan* pl = new Plan();
+        int r = build_plan(*pl);
+        if (r != 0) {
+            delete pl;
+            return r;
+        }
+        pl->B = B, pl->Lmax = Lmax, pl->gen = g_alloc_generation;
+        w->plans.insert(w->plans.begin(), pl);
+        while (w->plans.size() > 4) {
+            delete w->plans.back();
+            w->plans.pop_back();
+        }
+        plan = pl;
+    }
+    return 0;
+}
+
+int Fwd::build_plan(Plan& pl) {
+    const s3b_config& c = m->cfg;
+    const int D = c.embed_dim, F = c.ffn_dim, H = c.num_heads, NL = c.num_layers, C = kConvDim;
     for (int i = 1; i < kNumConv; ++i) {
-        S3B_OK(conv_params(p, m->act[i - 1].h(), m->act[i - 1].l(), m->conv_w[i].h(), m->conv_w[i].l(), B, L[i - 1],
+        GemmParams& p = pl.conv[i];
+        S3B_OK(conv_params(p, w->act[i - 1].h(), w->act[i - 1].l(), m->conv_w[i].h(), m->conv_w[i].l(), B, L[i - 1],
                            L[i], kConvK[i]));
         Epi e;
         e.bias = c.conv_bias ? m->conv_b[i].as<float>() : nullptr;
         const bool last = (i == kNumConv - 1);
         if (c.extractor_layer_norm) {
-            e.out_f32 = m->conv_f32.as<float>();
+            e.out_f32 = w->conv_f32.as<float>();
         } else {
             e.gelu = 1;
-            if (last) e.out_f32 = m->conv_f32.as<float>();
-            else e.out_hi = m->act[i].h(), e.out_lo = m->act[i].l();
+            if (last) e.out_f32 = w->conv_f32.as<float>();
+            else e.out_hi = w->act[i].h(), e.out_lo = w->act[i].l();
         }
         set_epi(p, e, C);
-        KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
-        if (c.extractor_layer_norm) {
-            // per-frame LayerNorm(512) + GELU (wav2vec2_model.py:2887-2897)
-            KNORM(launch_layernorm(m->conv_f32.as<float>(), (size_t)B * L[i], C, m->conv_ln_g[i].as<float>(),
-                                     m->conv_ln_b[i].as<float>(), 1, last ? m->conv_f32.as<float>() : nullptr,
-                                     last ? nullptr : m->act[i].h(), last ? nullptr : m->act[i].l(), st));
-        }
     }
-
-    // ---- LayerNorm(512) -> post_extract_proj (+ zero padded frames) ------------------------------------------
-    KNORM(launch_layernorm(m->conv_f32.as<float>(), (size_t)M, C, m->ln512_g.as<float>(), m->ln512_b.as<float>(), 0,
-                             nullptr, m->ln512_s.h(), m->ln512_s.l(), st));
     {
-        S3B_OK(linear_params(p, m->ln512_s.h(), m->ln512_s.l(), m->proj_w.h(), m->proj_w.l(), M, D, C));
+        GemmParams& p = pl.proj;
+        S3B_OK(linear_params(p, w->ln512_s.h(), w->ln512_s.l(), m->proj_w.h(), m->proj_w.l(), M, D, C));
         Epi e;
         e.bias = m->proj_b.as<float>();
-        e.row_mask = m->rowmask_dev.as<uint8_t>();  // x[padding_mask] = 0 (wav2vec2_model.py:3061-3062)
-        e.out_f32 = m->x_f32.as<float>();
-        e.out_hi = m->x_s.h(), e.out_lo = m->x_s.l();
+        e.row_mask = d_mask;  // x[padding_mask] = 0 (wav2vec2_model.py:3061-3062)
+        e.out_f32 = w->x_f32.as<float>();
+        e.out_hi = w->x_s.h(), e.out_lo = w->x_s.l();
         set_epi(p, e, D);
-        KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
     }
-
-    // ---- x = x + GELU(pos_conv(x)) ; post-LN models: LayerNorm -> hidden state 0 ------------------------------
-    float* hs0 = hidden_out;
-    const size_t hs_stride = (size_t)M * D;
     {
+        GemmParams& p = pl.pos;
         if (posconv4_ok(c)) {
-            S3B_OK(m->pos_z.ensure((size_t)B * (T + 3) * 4 * D * sizeof(float)));
-            S3B_OK(posconv4_params(p, c, m->x_s.h(), m->x_s.l(), m->pos_w4.h(), m->pos_w4.l(), B, T));
+            S3B_OK(posconv4_params(p, c, w->x_s.h(), w->x_s.l(), m->pos_w4.h(), m->pos_w4.l(), B, T));
             Epi e;
-            e.out_f32 = m->pos_z.as<float>();
+            e.out_f32 = w->pos_z.as<float>();
             set_epi(p, e, 4 * D);
-            KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
-            const bool ln = !c.layer_norm_first;
-            KNORM(launch_posconv_combine(m->pos_z.as<float>(), m->x_f32.as<float>(), m->pos_b.as<float>(), B, T, D,
-                                           D / c.pos_conv_groups, m->enc_ln_g.as<float>(), m->enc_ln_b.as<float>(),
-                                           ln ? 1 : 0, hs0, ln ? m->xs_s.h() : nullptr, ln ? m->xs_s.l() : nullptr, st));
         } else {
-            S3B_OK(posconv_params(p, c, m->x_s.h(), m->x_s.l(), m->pos_w.h(), m->pos_w.l(), B, T));
+            S3B_OK(posconv_params(p, c, w->x_s.h(), w->x_s.l(), m->pos_w.h(), m->pos_w.l(), B, T));
             Epi e;
             e.bias = m->pos_b.as<float>();
             e.gelu = 1;
-            e.residual = m->x_f32.as<float>();
-            e.out_f32 = c.layer_norm_first ? hs0 : m->tmp_f32.as<float>();
+            e.residual = w->x_f32.as<float>();
+            e.out_f32 = w->tmp_f32.as<float>();  // pre-LN: patched to hidden state 0 per call
             set_epi(p, e, D);
-            KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
-            if (!c.layer_norm_first)
-                KNORM(launch_layernorm(m->tmp_f32.as<float>(), (size_t)M, D, m->enc_ln_g.as<float>(),
-                                         m->enc_ln_b.as<float>(), 0, hs0, m->xs_s.h(), m->xs_s.l(), st));
-        }
-        if (layer_done) S3B_OK(layer_done(m, 0, st, user));
-    }
-
-    // ---- WavLM relative position table (ungated, shared by all layers; WavLM.py:622-632) -----------------------
-    const bool rel = c.relative_position != 0;
-    if (rel) {
-        S3B_OK(m->rel_table.ensure((size_t)H * (2 * T - 1) * 4));
-        S3B_OK(m->gate.ensure((size_t)B * H * T * 4));
-        if (m->rel_table_T != T) {
-            KMISC(launch_wavlm_rel_table(m->rel_table_src.as<float>(), c.num_buckets, c.max_distance, H, T,
-                                           m->rel_table.as<float>(), st));
-            m->rel_table_T = T;
         }
     }
-
-    // ---- transformer layers -------------------------------------------------------------------------
+    pl.layers.resize(NL);
+    const uint64_t BH = (uint64_t)B * H;
     for (int l = 0; l < NL; ++l) {
         LayerW& W = m->layers[l];
-        float* hs_in = hidden_out + (size_t)l * hs_stride;        // layer input = hidden state l
-        float* hs_out = hidden_out + (size_t)(l + 1) * hs_stride;  // hidden state l+1
-        const bool last = (l == NL - 1);
-
-        if (c.layer_norm_first)  // xs = LN1(residual stream)
-            KNORM(launch_layernorm(hs_in, (size_t)M, D, W.ln1_g.as<float>(), W.ln1_b.as<float>(), 0, nullptr,
-                                     m->xs_s.h(), m->xs_s.l(), st));
-        // QKV projection, scattered per head; q pre-scaled by head_dim^-0.5 (exact power of two)
-        S3B_OK(linear_params(p, m->xs_s.h(), m->xs_s.l(), W.qkv.h(), W.qkv.l(), M, 3 * D, D));
-        {
+        LayerPlan& lp = pl.layers[l];
+        {   // QKV projection, scattered per head; q pre-scaled by head_dim^-0.5 (exact power of two) and log2(e)
+            GemmParams& p = lp.qkv;
+            S3B_OK(linear_params(p, w->xs_s.h(), w->xs_s.l(), W.qkv.h(), W.qkv.l(), M, 3 * D, D));
             Epi e;
             e.bias = W.qkv_b.as<float>();
             set_epi(p, e, 3 * D);
-            // head_dim^-0.5 and log2(e): the attention kernel's softmax works in the exp2 domain
             p.qkv_mode = 1, p.T = T, p.Tp = Tp, p.H = H, p.D = D, p.q_scale = 0.125f * 1.4426950408889634f;
-            p.q_hi = m->q_s.h(), p.q_lo = m->q_s.l(), p.k_hi = m->k_s.h(), p.k_lo = m->k_s.l();
-            p.vt_hi = m->vt_s.h(), p.vt_lo = m->vt_s.l();
+            p.q_hi = w->q_s.h(), p.q_lo = w->q_s.l(), p.k_hi = w->k_s.h(), p.k_lo = w->k_s.l();
+            p.vt_hi = w->vt_s.h(), p.vt_lo = w->vt_s.l();
         }
-        KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
-
-        AttnParams ap;
-        memset(&ap, 0, sizeof(ap));
-        const uint64_t BH = (uint64_t)B * H;
-        TMAP_OK(encode_tmap_bf16_3d(&ap.q_hi, m->q_s.h(), 64, T, BH, 64, (uint64_t)T * 64, 64, 128));
-        TMAP_OK(encode_tmap_bf16_3d(&ap.q_lo, m->q_s.l(), 64, T, BH, 64, (uint64_t)T * 64, 64, 128));
-        TMAP_OK(encode_tmap_bf16_3d(&ap.k_hi, m->k_s.h(), 64, T, BH, 64, (uint64_t)T * 64, 64, 64));
-        TMAP_OK(encode_tmap_bf16_3d(&ap.k_lo, m->k_s.l(), 64, T, BH, 64, (uint64_t)T * 64, 64, 64));
-        TMAP_OK(encode_tmap_bf16_3d(&ap.vt_hi, m->vt_s.h(), T, 64, BH, Tp, (uint64_t)64 * Tp, 64, 64));
-        TMAP_OK(encode_tmap_bf16_3d(&ap.vt_lo, m->vt_s.l(), T, 64, BH, Tp, (uint64_t)64 * Tp, 64, 64));
-        ap.B = B, ap.H = H, ap.T = T, ap.D = D;
-        ap.kv_len = m->kvlen_dev.as<int>();
-        if (rel) {
-            ap.bias_table = m->rel_table.as<float>();
-            // gate from the layer's attention input (post-LN: hs_in; pre-LN: LN1 output) wavlm/modules.py:534-551
-            KMISC(launch_wavlm_gate(m->xs_s.h(), m->xs_s.l(), (size_t)M, B, T, H, D,
-                                      c.gru_rel_pos ? W.grep_w.as<float>() : nullptr, W.grep_b.as<float>(),
-                                      W.grep_a.as<float>(), m->gate.as<float>(), st));
-            ap.gate = m->gate.as<float>();
-        }
-        ap.ctx_hi = m->ctx_s.h(), ap.ctx_lo = m->ctx_s.l();
-        KATTN(launch_attention(ap, st));
-
-        // out_proj + residual
-        S3B_OK(linear_params(p, m->ctx_s.h(), m->ctx_s.l(), W.out.h(), W.out.l(), M, D, D));
         {
+            AttnParams& ap = lp.attn;
+            memset(&ap, 0, sizeof(ap));
+            TMAP_OK(encode_tmap_bf16_3d(&ap.q_hi, w->q_s.h(), 64, T, BH, 64, (uint64_t)T * 64, 64, 128));
+            TMAP_OK(encode_tmap_bf16_3d(&ap.q_lo, w->q_s.l(), 64, T, BH, 64, (uint64_t)T * 64, 64, 128));
+            TMAP_OK(encode_tmap_bf16_3d(&ap.k_hi, w->k_s.h(), 64, T, BH, 64, (uint64_t)T * 64, 64, 64));
+            TMAP_OK(encode_tmap_bf16_3d(&ap.k_lo, w->k_s.l(), 64, T, BH, 64, (uint64_t)T * 64, 64, 64));
+            TMAP_OK(encode_tmap_bf16_3d(&ap.vt_hi, w->vt_s.h(), T, 64, BH, Tp, (uint64_t)64 * Tp, 64, 64));
+            TMAP_OK(encode_tmap_bf16_3d(&ap.vt_lo, w->vt_s.l(), T, 64, BH, Tp, (uint64_t)64 * Tp, 64, 64));
+            ap.B = B, ap.H = H, ap.T = T, ap.D = D;
+            ap.kv_len = d_kv;
+            if (c.relative_position) {
+                ap.bias_table = m->rel_table.as<float>();
+                ap.bias_stride = 2 * m->rel_table_T - 1, ap.bias_center = m->rel_table_T - 1;
+                ap.gate = w->gate.as<float>();
+            }
+            ap.ctx_hi = w->ctx_s.h(), ap.ctx_lo = w->ctx_s.l();
+        }
+        {   // out_proj + residual (residual = hidden state l, patched per call)
+            GemmParams& p = lp.out;
+            S3B_OK(linear_params(p, w->ctx_s.h(), w->ctx_s.l(), W.out.h(), W.out.l(), M, D, D));
             Epi e;
             e.bias = W.out_b.as<float>();
-            e.residual = hs_in;
-            e.out_f32 = c.layer_norm_first ? m->x1_f32.as<float>() : m->tmp_f32.as<float>();
+            e.out_f32 = c.layer_norm_first ? w->x1_f32.as<float>() : w->tmp_f32.as<float>();
             set_epi(p, e, D);
         }
-        KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
-        if (c.layer_norm_first)  // x1_s = LN2(r1), r1 = x1_f32
-            KNORM(launch_layernorm(m->x1_f32.as<float>(), (size_t)M, D, W.ln2_g.as<float>(), W.ln2_b.as<float>(), 0,
-                                     nullptr, m->x1_s.h(), m->x1_s.l(), st));
-        else  // x1 = LN1(x + attn)
-            KNORM(launch_layernorm(m->tmp_f32.as<float>(), (size_t)M, D, W.ln1_g.as<float>(), W.ln1_b.as<float>(), 0,
-                                     m->x1_f32.as<float>(), m->x1_s.h(), m->x1_s.l(), st));
-        // fc1 + GELU
-        S3B_OK(linear_params(p, m->x1_s.h(), m->x1_s.l(), W.fc1.h(), W.fc1.l(), M, F, D));
-        {
+        {   // fc1 + GELU
+            GemmParams& p = lp.fc1;
+            S3B_OK(linear_params(p, w->x1_s.h(), w->x1_s.l(), W.fc1.h(), W.fc1.l(), M, F, D));
             Epi e;
             e.bias = W.fc1_b.as<float>();
             e.gelu = 1;
-            e.out_hi = m->h_s.h(), e.out_lo = m->h_s.l();
+            e.out_hi = w->h_s.h(), e.out_lo = w->h_s.l();
             set_epi(p, e, F);
         }
-        KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
-        // fc2 + residual
-        S3B_OK(linear_params(p, m->h_s.h(), m->h_s.l(), W.fc2.h(), W.fc2.l(), M, D, F));
-        {
+        {   // fc2 + residual (output patched per call for pre-LN models)
+            GemmParams& p = lp.fc2;
+            S3B_OK(linear_params(p, w->h_s.h(), w->h_s.l(), W.fc2.h(), W.fc2.l(), M, D, F));
             Epi e;
             e.bias = W.fc2_b.as<float>();
-            e.residual = m->x1_f32.as<float>();
-            // pre-LN: the sum IS hidden state l+1 (un-normalised residual stream), except after the last layer
-            e.out_f32 = (c.layer_norm_first && !last) ? hs_out : m->tmp_f32.as<float>();
+            e.residual = w->x1_f32.as<float>();
+            e.out_f32 = w->tmp_f32.as<float>();
             set_epi(p, e, D);
         }
-        KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
-        if (c.layer_norm_first) {
-            if (last)  // encoder.layer_norm on the final output (wav2vec2_model.py:3049-3050)
-                KNORM(launch_layernorm(m->tmp_f32.as<float>(), (size_t)M, D, m->enc_ln_g.as<float>(),
-                                         m->enc_ln_b.as<float>(), 0, hs_out, nullptr, nullptr, st));
+    }
+    return 0;
+}
+
+int Fwd::stage(int s) {
+    s3b_model* m = this->m;  // the launch macros expect `m` and `st`
+    cudaStream_t st = this->st;
+    const s3b_config& c = m->cfg;
+    const int D = c.embed_dim, H = c.num_heads, NL = c.num_layers, C = kConvDim;
+    const double attn_flops = 4.0 * (double)T * T * D * B;
+    const double conv0_flops = 2.0 * kConvK[0] * C * (double)B * L[0];
+
+    if (s == 0) {
+        // ---- bookkeeping copy, waveform packing (+ normalisation), conv 0 + norm + GELU -> act[0] ------------------
+        const size_t book_bytes = (size_t)(reinterpret_cast<char*>(d_mask) - w->book.as<char>()) + (size_t)M;
+        CUDA_OK(cudaMemcpyAsync(w->book.p, w->book_host, book_bytes, cudaMemcpyHostToDevice, st));
+        CUDA_OK(cudaEventRecord(w->book_copied, st));
+        KMISC(launch_wav_pack(d_wavs, d_lens, B, Lmax, c.normalize_wav, w->wav_stats.as<float>(),
+                              w->wav_pad.as<float>(), st));
+        if (c.extractor_layer_norm) {
+            KCONV0(1, launch_conv0_layernorm(w->wav_pad.as<float>(), B, Lmax, (int)L[0], m->conv0_w.as<float>(),
+                                             c.conv_bias ? m->conv0_b.as<float>() : nullptr, m->norm0_g.as<float>(),
+                                             m->norm0_b.as<float>(), w->act[0].h(), w->act[0].l(), st));
         } else {
-            KNORM(launch_layernorm(m->tmp_f32.as<float>(), (size_t)M, D, W.ln2_g.as<float>(), W.ln2_b.as<float>(), 0,
-                                     hs_out, last ? nullptr : m->xs_s.h(), last ? nullptr : m->xs_s.l(), st));
+            // a conv-0 bias (conv_bias with extractor_mode "default") is removed again by the per-channel GroupNorm
+            // mean: it cancels exactly in (z + b) - mean(z + b), so the kernel never adds it
+            KCONV0(3, launch_conv0_groupnorm(w->wav_pad.as<float>(), B, Lmax, (int)L[0], m->conv0_w.as<float>(),
+                                             m->norm0_g.as<float>(), m->norm0_b.as<float>(), w->c0_part.as<float>(),
+                                             w->c0_ss.as<float>(), w->act[0].h(), w->act[0].l(), st));
         }
-        if (layer_done) S3B_OK(layer_done(m, l + 1, st, user));
+        return 0;
+    }
+    if (s >= 1 && s <= 6) {
+        // ---- conv s as implicit GEMM (+ per-frame LayerNorm + GELU in "layer_norm" mode) ----------------------------
+        const int i = s;
+        GemmParams p = plan->conv[i];
+        KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
+        if (c.extractor_layer_norm) {
+            const bool last = (i == kNumConv - 1);
+            KNORM(launch_layernorm(w->conv_f32.as<float>(), (size_t)B * L[i], C, m->conv_ln_g[i].as<float>(),
+                                   m->conv_ln_b[i].as<float>(), 1, last ? w->conv_f32.as<float>() : nullptr,
+                                   last ? nullptr : w->act[i].h(), last ? nullptr : w->act[i].l(), st));
+        }
+        return 0;
+    }
+    if (s == 7) {
+        // ---- LayerNorm(512) -> post_extract_proj (+ zero padded frames) --------------------------------------------
+        KNORM(launch_layernorm(w->conv_f32.as<float>(), (size_t)M, C, m->ln512_g.as<float>(), m->ln512_b.as<float>(),
+                               0, nullptr, w->ln512_s.h(), w->ln512_s.l(), st));
+        GemmParams p = plan->proj;
+        KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
+        return 0;
+    }
+    if (s == 8) {
+        // ---- x = x + GELU(pos_conv(x)) ; post-LN models: LayerNorm -> hidden state 0 -------------------------------
+        GemmParams p = plan->pos;
+        float* hs0 = hs(0);
+        if (posconv4_ok(c)) {
+            KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
+            const bool ln = !c.layer_norm_first;
+            KNORM(launch_posconv_combine(w->pos_z.as<float>(), w->x_f32.as<float>(), m->pos_b.as<float>(), B, T, D,
+                                         D / c.pos_conv_groups, m->enc_ln_g.as<float>(), m->enc_ln_b.as<float>(),
+                                         ln ? 1 : 0, hs0, ln ? w->xs_s.h() : nullptr, ln ? w->xs_s.l() : nullptr, st));
+        } else {
+            if (c.layer_norm_first) p.out_f32 = hs0;
+            KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
+            if (!c.layer_norm_first)
+                KNORM(launch_layernorm(w->tmp_f32.as<float>(), (size_t)M, D, m->enc_ln_g.as<float>(),
+                                       m->enc_ln_b.as<float>(), 0, hs0, w->xs_s.h(), w->xs_s.l(), st));
+        }
+        if (layer_done) S3B_OK(layer_done(m, 0, st, user));
+        return 0;
+    }
+
+    // ---- transformer layer l, five stages ---------------------------------------------------------------------
+    const int l = (s - 9) / 5, sub = (s - 9) % 5;
+    if (l >= NL) return fail("internal: stage %d out of range", s);
+    LayerW& W = m->layers[l];
+    LayerPlan& lp = plan->layers[l];
+    float* hs_in = hs(l);       // layer input = hidden state l
+    float* hs_out = hs(l + 1);  // hidden state l+1
+    const bool last = (l == NL - 1);
+    const bool rel = c.relative_position != 0;
+    switch (sub) {
+        case 0: {
+            if (c.layer_norm_first)  // xs = LN1(residual stream)
+                KNORM(launch_layernorm(hs_in, (size_t)M, D, W.ln1_g.as<float>(), W.ln1_b.as<float>(), 0, nullptr,
+                                       w->xs_s.h(), w->xs_s.l(), st));
+            GemmParams p = lp.qkv;
+            KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
+            if (rel)  // gate from the layer's attention input (post-LN: hs_in; pre-LN: LN1 output) modules.py:534-551
+                KMISC(launch_wavlm_gate(w->xs_s.h(), w->xs_s.l(), (size_t)M, B, T, H, D,
+                                        c.gru_rel_pos ? W.grep_w.as<float>() : nullptr, W.grep_b.as<float>(),
+                                        W.grep_a.as<float>(), w->gate.as<float>(), st));
+            return 0;
+        }
+        case 1: {
+            KATTN(launch_attention(lp.attn, st));
+            return 0;
+        }
+        case 2: {
+            GemmParams p = lp.out;
+            p.residual = hs_in;
+            KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
+            if (c.layer_norm_first)  // x1_s = LN2(r1), r1 = x1_f32
+                KNORM(launch_layernorm(w->x1_f32.as<float>(), (size_t)M, D, W.ln2_g.as<float>(), W.ln2_b.as<float>(), 0,
+                                       nullptr, w->x1_s.h(), w->x1_s.l(), st));
+            else  // x1 = LN1(x + attn)
+                KNORM(launch_layernorm(w->tmp_f32.as<float>(), (size_t)M, D, W.ln1_g.as<float>(), W.ln1_b.as<float>(), 0,
+                                       w->x1_f32.as<float>(), w->x1_s.h(), w->x1_s.l(), st));
+            return 0;
+        }
+        case 3: {
+            GemmParams p = lp.fc1;
+            KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
+            return 0;
+        }
+        default: {
+            GemmParams p = lp.fc2;
+            // pre-LN: the sum IS hidden state l+1 (un-normalised residual stream), except after the last layer
+            float* unnorm = (last && last_res != nullptr) ? last_res : w->tmp_f32.as<float>();
+            if (c.layer_norm_first) p.out_f32 = last ? unnorm : hs_out;
+            if (ffn_out != nullptr) p.out_pre = ffn_out + (size_t)l * ffn_stride;
+            KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
+            if (c.layer_norm_first) {
+                if (last)  // encoder.layer_norm on the final output (wav2vec2_model.py:3049-3050)
+                    KNORM(launch_layernorm(unnorm, (size_t)M, D, m->enc_ln_g.as<float>(), m->enc_ln_b.as<float>(), 0,
+                                           hs_out, nullptr, nullptr, st));
+            } else {
+                KNORM(launch_layernorm(w->tmp_f32.as<float>(), (size_t)M, D, W.ln2_g.as<float>(), W.ln2_b.as<float>(), 0,
+                                       hs_out, last ? nullptr : w->xs_s.h(), last ? nullptr : w->xs_s.l(), st));
+            }
+            if (layer_done) S3B_OK(layer_done(m, l + 1, st, user));
+            return 0;
+        }
+    }
+    return 0;
+}
+
+// Number of lanes for a batch: S3B_LANES overrides; otherwise two lanes whenever the batch can be split.
+static int default_lanes(int B) {
+    static int env = -2;
+    if (env == -2) {
+        const char* e = getenv("S3B_LANES");
+        env = e ? atoi(e) : -1;
+    }
+    int lanes = env > 0 ? env : 2;
+    if (lanes > 2) lanes = 2;
+    if (B < 2) lanes = 1;
+    return lanes;
+}
+
+static int forward_lanes(s3b_model* m, const float* const* wavs, const int64_t* lens, int B, int64_t Lmax,
+                         float* hidden_out, cudaStream_t st, const s3b_forward_opts* o) {
+    const s3b_config& c = m->cfg;
+    if (B < 1) return fail("empty batch");
+    const int64_t T = num_frames(Lmax);
+    if (T < 1) return fail("max_len %lld too short: the conv stack yields no frame", (long long)Lmax);
+    int lanes = (o && o->lanes > 0) ? o->lanes : default_lanes(B);
+    if (lanes > 2) lanes = 2;
+    if (lanes > B) lanes = B;
+    const size_t frame = (size_t)T * c.embed_dim;
+    const size_t layer_stride = (o && o->layer_stride > 0) ? (size_t)o->layer_stride : (size_t)B * frame;
+    float* ffn_out = o ? o->ffn_out : nullptr;
+    const size_t ffn_stride = (o && o->ffn_layer_stride > 0) ? (size_t)o->ffn_layer_stride : (size_t)B * frame;
+    float* last_res = o ? o->last_residual : nullptr;
+
+    Fwd f[2];
+    int b0 = 0;
+    for (int i = 0; i < lanes; ++i) {
+        const int nb = (i == 0) ? (B + lanes - 1) / lanes : B - b0;
+        f[i].m = m, f[i].w = &m->ws[i], f[i].wavs = wavs + b0, f[i].lens = lens + b0, f[i].B = nb, f[i].Lmax = Lmax;
+        f[i].hidden = hidden_out + (size_t)b0 * frame, f[i].layer_stride = layer_stride;
+        f[i].ffn_out = ffn_out ? ffn_out + (size_t)b0 * frame : nullptr, f[i].ffn_stride = ffn_stride;
+        f[i].last_res = last_res ? last_res + (size_t)b0 * frame : nullptr;
+        f[i].st = st;
+        b0 += nb;
+    }
+    // profiling brackets every launch with events: lanes then run one after the other on the caller's stream so that
+    // each kernel is timed alone, at its production shape
+    const bool concurrent = lanes == 2 && !m->prof.on;
+    if (concurrent) {
+        Workspace& w1 = m->ws[1];
+        if (w1.stream == nullptr) CUDA_OK(cudaStreamCreateWithFlags(&w1.stream, cudaStreamNonBlocking));
+        if (w1.done == nullptr) CUDA_OK(cudaEventCreateWithFlags(&w1.done, cudaEventDisableTiming));
+        if (m->fork_event == nullptr) CUDA_OK(cudaEventCreateWithFlags(&m->fork_event, cudaEventDisableTiming));
+        f[1].st = w1.stream;
+    }
+    for (int i = 0; i < lanes; ++i) S3B_OK(f[i].prepare());
+    if (concurrent) {
+        CUDA_OK(cudaEventRecord(m->fork_event, st));
+        CUDA_OK(cudaStreamWaitEvent(f[1].st, m->fork_event, 0));
+    }
+    const int ns = f[0].num_stages();
+    if (concurrent) {
+        // lane 1 trails lane 0 by two stages: while one lane runs a GEMM the other tends to be in a different kind of
+        // kernel (attention, LayerNorm, another GEMM shape), which is what lets them share the SMs
+        for (int s = 0; s < ns + 2; ++s) {
+            if (s < ns) S3B_OK(f[0].stage(s));
+            if (s >= 2) S3B_OK(f[1].stage(s - 2));
+        }
+        CUDA_OK(cudaEventRecord(m->ws[1].done, f[1].st));
+        CUDA_OK(cudaStreamWaitEvent(st, m->ws[1].done, 0));
+    } else {
+        for (int i = 0; i < lanes; ++i)
+            for (int s = 0; s < ns; ++s) S3B_OK(f[i].stage(s));
     }
     return 0;
 }
@@ -906,20 +1199,34 @@ extern "C" int s3b_forward(s3b_model* m, const float* const* wavs, const int64_t
                            int64_t max_len, float* hidden_out, void* stream) {
     if (!m || !wavs || !lens || !hidden_out) return fail("null argument");
     if (!m->finalized) return fail("model not finalized");
-    return forward_impl(m, wavs, lens, batch, max_len, hidden_out, (cudaStream_t)stream);
+    return forward_lanes(m, wavs, lens, batch, max_len, hidden_out, (cudaStream_t)stream, nullptr);
 }
 
-extern "C" int s3b_forward_host(s3b_model* m, const float* const* wavs, const int64_t* lens, int32_t batch,
-                                int64_t max_len, float* hidden_out) {
+extern "C" int s3b_forward_ex(s3b_model* m, const float* const* wavs, const int64_t* lens, int32_t batch,
+                              int64_t max_len, float* hidden_out, void* stream, const s3b_forward_opts* opts) {
     if (!m || !wavs || !lens || !hidden_out) return fail("null argument");
     if (!m->finalized) return fail("model not finalized");
+    if (opts != nullptr && opts->struct_size != (int32_t)sizeof(s3b_forward_opts))
+        return fail("s3b_forward_opts.struct_size %d != %d (header / library mismatch)", opts->struct_size,
+                    (int)sizeof(s3b_forward_opts));
+    for (int b = 0; b < batch; ++b)
+        if (lens[b] > max_len) return fail("lens[%d]=%lld exceeds max_len", b, (long long)lens[b]);
+    return forward_lanes(m, wavs, lens, batch, max_len, hidden_out, (cudaStream_t)stream, opts);
+}
+
+static int forward_host_impl(s3b_model* m, const float* const* wavs, const int64_t* lens, int32_t batch,
+                             int64_t max_len, float* hidden_out, float* hidden_dev) {
     const int64_t T = num_frames(max_len);
     if (T < 1) return fail("max_len too short");
     size_t total = 0;
     for (int b = 0; b < batch; ++b) total += (size_t)lens[b];
     S3B_OK(m->stage_wav.ensure(total * 4));
-    const size_t out_elems = (size_t)(m->cfg.num_layers + 1) * batch * T * m->cfg.embed_dim;
-    S3B_OK(m->stage_out.ensure(out_elems * 4));
+    const size_t frame_elems = (size_t)T * m->cfg.embed_dim;
+    const size_t layer_elems = (size_t)batch * frame_elems;
+    if (hidden_dev == nullptr) {
+        S3B_OK(m->stage_out.ensure((size_t)(m->cfg.num_layers + 1) * layer_elems * 4));
+        hidden_dev = m->stage_out.as<float>();
+    }
     if (m->copy_stream == nullptr) CUDA_OK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
     if (m->compute_stream == nullptr) CUDA_OK(cudaStreamCreateWithFlags(&m->compute_stream, cudaStreamNonBlocking));
     while ((int)m->layer_events.size() < m->cfg.num_layers + 1) {
@@ -940,19 +1247,20 @@ extern "C" int s3b_forward_host(s3b_model* m, const float* const* wavs, const in
     // The batch is processed as k utterance chunks (S3B_HOST_CHUNKS=k overrides the default below) so that chunk
     // c+1's conv stack overlaps chunk c's copies — nothing can leave the device before the first
     // hidden state exists (~5 ms at 32 x 10 s), which is what bounds the end-to-end time. Utterances
-    // are independent given the shared max_len, so the result is bit-identical.
+    // are independent given the shared max_len, so the result is bit-identical. Every chunk writes its utterances'
+    // slice of the standard [NL+1][batch][T][D] device buffer (layer stride = the whole batch).
     struct Ctx {
         float* host;        // hidden_out + first utterance of the chunk
-        const float* dev;   // this chunk's [NL+1][Bc][T][D] region of the staging buffer
-        size_t host_layer;  // elements between layers in the host buffer  (batch * T * D)
-        size_t chunk_layer; // elements per layer of this chunk            (Bc * T * D)
+        const float* dev;   // same position in the device buffer
+        size_t layer;       // elements between layers (batch * T * D), host and device alike
+        size_t chunk;       // elements per layer of this chunk (Bc * T * D)
     };
     auto layer_done = [](s3b_model* mm, int l, cudaStream_t s, void* user) -> int {
         Ctx* c = static_cast<Ctx*>(user);
         CUDA_OK(cudaEventRecord(mm->layer_events[l], s));
         CUDA_OK(cudaStreamWaitEvent(mm->copy_stream, mm->layer_events[l], 0));
-        CUDA_OK(cudaMemcpyAsync(c->host + (size_t)l * c->host_layer, c->dev + (size_t)l * c->chunk_layer,
-                                c->chunk_layer * 4, cudaMemcpyDeviceToHost, mm->copy_stream));
+        CUDA_OK(cudaMemcpyAsync(c->host + (size_t)l * c->layer, c->dev + (size_t)l * c->layer, c->chunk * 4,
+                                cudaMemcpyDeviceToHost, mm->copy_stream));
         return 0;
     };
     // default: two chunks from 16 utterances on (first-output latency ~ half, GEMMs at 16 utterances still run at
@@ -961,20 +1269,35 @@ extern "C" int s3b_forward_host(s3b_model* m, const float* const* wavs, const in
     if (const char* e = getenv("S3B_HOST_CHUNKS")) chunks = atoi(e);
     if (chunks < 1) chunks = 1;
     if (chunks > batch) chunks = batch;
-    const size_t frame_elems = (size_t)T * m->cfg.embed_dim;
     std::vector<Ctx> ctxs(chunks);
-    size_t dev_off = 0;
     for (int c = 0; c < chunks; ++c) {
         const int b0 = (int)((int64_t)batch * c / chunks), b1 = (int)((int64_t)batch * (c + 1) / chunks);
-        const int bc = b1 - b0;
-        float* dev = m->stage_out.as<float>() + dev_off;
-        ctxs[c] = Ctx{hidden_out + (size_t)b0 * frame_elems, dev, (size_t)batch * frame_elems, (size_t)bc * frame_elems};
-        S3B_OK(forward_impl(m, ptrs.data() + b0, lens + b0, bc, max_len, dev, st, layer_done, &ctxs[c]));
-        dev_off += (size_t)(m->cfg.num_layers + 1) * bc * frame_elems;
+        ctxs[c] = Ctx{hidden_out + (size_t)b0 * frame_elems, hidden_dev + (size_t)b0 * frame_elems, layer_elems,
+                      (size_t)(b1 - b0) * frame_elems};
+        Fwd f;
+        f.m = m, f.w = &m->ws[0], f.st = st, f.wavs = ptrs.data() + b0, f.lens = lens + b0, f.B = b1 - b0;
+        f.Lmax = max_len, f.hidden = hidden_dev + (size_t)b0 * frame_elems, f.layer_stride = layer_elems;
+        f.layer_done = layer_done, f.user = &ctxs[c];
+        S3B_OK(f.prepare());
+        for (int s = 0; s < f.num_stages(); ++s) S3B_OK(f.stage(s));
     }
     CUDA_OK(cudaStreamSynchronize(st));
     CUDA_OK(cudaStreamSynchronize(m->copy_stream));
     return 0;
+}
+
+extern "C" int s3b_forward_host(s3b_model* m, const float* const* wavs, const int64_t* lens, int32_t batch,
+                                int64_t max_len, float* hidden_out) {
+    if (!m || !wavs || !lens || !hidden_out) return fail("null argument");
+    if (!m->finalized) return fail("model not finalized");
+    return forward_host_impl(m, wavs, lens, batch, max_len, hidden_out, nullptr);
+}
+
+extern "C" int s3b_forward_host_ex(s3b_model* m, const float* const* wavs, const int64_t* lens, int32_t batch,
+                                   int64_t max_len, float* hidden_out, float* hidden_out_dev) {
+    if (!m || !wavs || !lens || !hidden_out) return fail("null argument");
+    if (!m->finalized) return fail("model not finalized");
+    return forward_host_impl(m, wavs, lens, batch, max_len, hidden_out, hidden_out_dev);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -27,6 +27,9 @@ EXPORTED_SYMBOLS = [
     "s3b_valid_frames",
     "s3b_forward",
     "s3b_forward_host",
+    "s3b_forward_ex",
+    "s3b_forward_host_ex",
+    "s3b_wavlm_buckets",
     "s3b_profile_enable",
     "s3b_profile_read",
     "s3b_launch_count",
@@ -69,6 +72,24 @@ class S3BConfig(C.Structure):
     ]
 
 
+class S3BForwardOpts(C.Structure):
+    """Mirror of ``struct s3b_forward_opts``."""
+
+    _fields_ = [
+        ("struct_size", C.c_int32),
+        ("lanes", C.c_int32),
+        ("layer_stride", C.c_int64),
+        ("ffn_out", C.c_void_p),
+        ("ffn_layer_stride", C.c_int64),
+        ("last_residual", C.c_void_p),
+        ("reserved", C.c_int64 * 4),
+    ]
+
+    def __init__(self, **kw):
+        super().__init__(**kw)
+        self.struct_size = C.sizeof(S3BForwardOpts)
+
+
 FAMILY_HUBERT, FAMILY_WAV2VEC2, FAMILY_WAVLM = 0, 1, 2
 
 _lib: Optional[C.CDLL] = None
@@ -103,6 +124,9 @@ def load() -> C.CDLL:
     lib.s3b_valid_frames.argtypes = [vp, C.POINTER(i64), i32, i64, C.POINTER(i32)]
     lib.s3b_forward.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i32, i64, f32p, vp]
     lib.s3b_forward_host.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i32, i64, f32p]
+    lib.s3b_forward_ex.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i32, i64, f32p, vp, C.POINTER(S3BForwardOpts)]
+    lib.s3b_forward_host_ex.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i32, i64, f32p, f32p]
+    lib.s3b_wavlm_buckets.argtypes = [i32, i32, C.POINTER(i32), i32, C.POINTER(i32)]
     lib.s3b_profile_enable.argtypes = [vp, i32]
     lib.s3b_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64), i32]
     lib.s3b_launch_count.argtypes = [vp]

@@ -43,7 +43,10 @@ class S3PRLUpstream(nn.Module):
         if path_or_url is not None:
             conf["ckpt"] = path_or_url
         if randomize:
-            conf["seed"] = torch.seed() % (2**31)  # our upstreams own their weights: re-draw the fabricated ones
+            # the reference re-initialises the loaded model's parameters (nn/upstream.py:119-122). Our upstreams own
+            # their weights: draw a seed from the default generator (reproducible under torch.manual_seed, global
+            # seed untouched) and fabricate fresh weights — for the checkpoint's architecture when a path is given.
+            conf["randomize_seed"] = int(torch.randint(0, 2**31 - 1, ()).item())
         self.upstream = hub.ENTRIES[name](**conf)
         self.normalize = normalize
         # static facts; the reference discovers them with a pseudo forward (nn/upstream.py:124-128), which would

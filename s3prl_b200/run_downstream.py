@@ -89,17 +89,48 @@ def install_shims() -> list:
     return stubbed
 
 
-def inject() -> list:
-    """Import ``s3prl.hub`` (with shims) and replace its wav2vec2 / HuBERT / WavLM / fbank entries."""
+def inject(featurizer: bool = True) -> list:
+    """Import ``s3prl.hub`` (with shims) and replace its wav2vec2 / HuBERT / WavLM / fbank entries; with
+    ``featurizer`` also replace the ``Featurizer`` class the Runner instantiates (``Runner._get_featurizer``,
+    s3prl/downstream/runner.py:166-180 resolves the name imported at runner.py:24 from s3prl.upstream.interfaces) by
+    the fused one, so that config 5 trains the layer weights through ``s3b_weighted_sum[_backward]`` instead of
+    ``torch.stack`` + mul + sum over 13 x [B, T, D]."""
     install_shims()
     import s3prl.hub as ref_hub
 
     from . import hub as our_hub
 
-    return our_hub.install(ref_hub)
+    names = our_hub.install(ref_hub)
+    if featurizer:
+        import s3prl.upstream.interfaces as ref_interfaces
+
+        from .upstream.featurizer import Featurizer
+
+        ref_interfaces.Featurizer = Featurizer
+        try:
+            import s3prl.downstream.runner as ref_runner
+
+            ref_runner.Featurizer = Featurizer
+        except Exception as e:  # the runner's own optional imports (only needed for training)
+            print(f"[s3prl_b200] s3prl.downstream.runner not importable yet ({e}); Featurizer injected into "
+                  "s3prl.upstream.interfaces only", file=sys.stderr)
+        names = names + ["Featurizer"]
+    return names
+
+
+def reject_unsupported(argv) -> None:
+    """``-f/--upstream_trainable`` fine-tunes the upstream (run_downstream.py:65, runner.py:300-301). The B200
+    upstreams are inference-only, so the run would silently train with a frozen upstream: refuse up front."""
+    for a in argv:
+        if a == "--upstream_trainable" or (a.startswith("-") and not a.startswith("--") and "f" in a[1:] and a[1:].isalpha()):
+            raise SystemExit(
+                "s3prl_b200: -f/--upstream_trainable is not supported (the B200-native upstreams are frozen, "
+                "inference-only); run without it, as the SUPERB recipes do."
+            )
 
 
 def main():
+    reject_unsupported(sys.argv[1:])
     names = inject()
     print(f"[s3prl_b200] injected {len(names)} B200-native entries into s3prl.hub", file=sys.stderr)
     from s3prl import run_downstream

@@ -40,6 +40,10 @@ class ArchConfig:
 _BASE = ArchConfig(family="hubert")
 _LARGE = dict(encoder_layers=24, encoder_embed_dim=1024, encoder_ffn_embed_dim=4096, encoder_attention_heads=16)
 _LL60K = dict(extractor_mode="layer_norm", conv_bias=True, layer_norm_first=True, normalize=True, **_LARGE)
+# WavLM-Large / UniSpeech-SAT-Large: WavLMConfig's default conv_bias=False (WavLM.py:174) with extractor_mode
+# "layer_norm". (A real checkpoint loaded through *_local carries its own cfg; this table only shapes the fabricated
+# checkpoints, and the two variants give golden coverage of layer_norm with and without conv bias.)
+_WAVLM_LARGE = dict(_LL60K, conv_bias=False)
 _WAVLM = dict(family="wavlm", relative_position_embedding=True, gru_rel_pos=True)
 
 ARCHS: Dict[str, ArchConfig] = {
@@ -53,12 +57,12 @@ ARCHS: Dict[str, ArchConfig] = {
     # WavLM (s3prl/upstream/wavlm/hubconf.py:38-78)
     "wavlm_base": replace(_BASE, **_WAVLM),
     "wavlm_base_plus": replace(_BASE, **_WAVLM),
-    "wavlm_large": replace(_BASE, **_WAVLM, **_LL60K),
+    "wavlm_large": replace(_BASE, **_WAVLM, **_WAVLM_LARGE),
     # UniSpeech-SAT runs the WavLM model class without relative position bias
     # (s3prl/upstream/unispeech_sat/expert.py:20,37-38; hubconf.py:47-82)
     "unispeech_sat_base": replace(_BASE, family="wavlm"),
     "unispeech_sat_base_plus": replace(_BASE, family="wavlm"),
-    "unispeech_sat_large": replace(_BASE, family="wavlm", **_LL60K),
+    "unispeech_sat_large": replace(_BASE, family="wavlm", **_WAVLM_LARGE),
 }
 # Same-skeleton relatives: identical architecture, different pre-training data (only the checkpoint differs).
 for _alias, _arch in {

@@ -9,13 +9,22 @@ wavlm/expert.py:33-87 and the UpstreamBase result dict, s3prl/upstream/interface
     result["last_hidden_state"], result["hidden_state_{i}"]
     expert.get_downsample_rates("hidden_states")   # 320
 
-The forward is inference-only (frozen upstream, the configuration SUPERB uses); asking for gradients
-through it raises instead of silently returning constants.
+The forward is inference-only (frozen upstream, the configuration SUPERB uses). The module has no trainable
+parameters: a waveform that requires grad raises, a forward in training mode with autograd enabled warns once
+(``Runner`` calls ``.train()`` on the upstream only under ``-f/--upstream_trainable``, which the launcher
+``python -m s3prl_b200.run_downstream`` rejects up front).
+
+Factory kwargs of the reference experts that are honoured: ``feature_selection`` in {None, "fairseq_layers",
+"fairseq_layers_before_residual"} (wav2vec2/expert.py:35-39,81-93) and ``hooks=[(module_path, transform), ...]`` /
+``hook_postprocess`` of ``UpstreamBase`` (interfaces.py:74-98) for the module paths ``self.model.encoder.layers[i]``
+and ``self.model.encoder`` (the ones the reference experts themselves register).
 """
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Optional, Union
+import re
+import warnings
+from typing import Callable, Dict, List, Optional, Sequence, Tuple, Union
 
 import torch
 import torch.nn as nn
@@ -85,6 +94,10 @@ class _NativeModel:
             pass
 
 
+_LAYER_PATH = re.compile(r"^self\.model\.encoder\.layers\[(\d+)\]$")
+_FEATURE_SELECTIONS = (None, "fairseq_layers", "fairseq_layers_before_residual")
+
+
 class UpstreamExpert(nn.Module):
     def __init__(
         self,
@@ -94,6 +107,10 @@ class UpstreamExpert(nn.Module):
         seed: int = 0,
         state_dict: Optional[Dict[str, torch.Tensor]] = None,
         arch: Optional[ArchConfig] = None,
+        feature_selection: Optional[str] = None,
+        hooks: Optional[Sequence[Tuple[str, Callable]]] = None,
+        hook_postprocess: Optional[Callable] = None,
+        randomize_seed: Optional[int] = None,
         **kwargs,
     ):
         super().__init__()
@@ -101,11 +118,37 @@ class UpstreamExpert(nn.Module):
         family = (arch or get_arch(name)).family if (arch is not None or ckpt is None) else _family_of(name)
         if ckpt is not None:
             self.arch, sd = load_reference_checkpoint(ckpt, family)
+            if randomize_seed is not None:  # S3PRLUpstream(randomize=True): the ckpt's architecture, fresh weights
+                sd = fabricate_state_dict(self.arch, randomize_seed)
         else:
             self.arch = arch or get_arch(name)
+            if randomize_seed is not None:
+                seed = randomize_seed
             sd = state_dict if state_dict is not None else fabricate_state_dict(self.arch, seed)
+        # wav2vec2/expert.py:35-39: only the wav2vec 2.0 expert takes feature_selection
+        if feature_selection not in _FEATURE_SELECTIONS:
+            raise AssertionError(f"feature_selection must be one of {_FEATURE_SELECTIONS}, got {feature_selection!r}")
+        if feature_selection is not None and self.arch.family != "wav2vec2":
+            raise TypeError(f"feature_selection is an option of the wav2vec2 experts only (got family {self.arch.family})")
+        self.feature_selection = feature_selection
+        # UpstreamBase hooks (interfaces.py:74-98): (module_path, transform(input, output)); supported module paths
+        # are the ones the reference experts register themselves
+        self.hooks: List[Tuple[str, Callable]] = []
+        for path, transform in hooks or []:
+            if not (_LAYER_PATH.match(path) or path == "self.model.encoder"):
+                raise ValueError(
+                    f"hook on '{path}' is not available: the native model exposes self.model.encoder.layers[i] "
+                    "and self.model.encoder"
+                )
+            m_ = _LAYER_PATH.match(path)
+            if m_ and int(m_.group(1)) >= self.arch.encoder_layers:
+                raise ValueError(f"hook on '{path}': the model has {self.arch.encoder_layers} layers")
+            self.hooks.append((path, transform))
+        self.hook_postprocess = hook_postprocess
         self._state_dict_host = sd  # kept on the host until the first device placement
         self._native: Optional[_NativeModel] = None
+        self._warned_grad = False
+        self.lanes = 0  # 0 = library default; 1 / 2 = utterance micro-batches on that many streams
         self.global_max_len: Optional[int] = None  # set when a batch is sharded across ranks
         # a buffer so that .to(device) / .cuda() tell us where to live, like any nn.Module
         self.register_buffer("_device_anchor", torch.zeros(1), persistent=False)
@@ -172,6 +215,15 @@ class UpstreamExpert(nn.Module):
                 "s3prl_b200 upstreams are inference-only (frozen upstream); gradients w.r.t. the waveform "
                 "or upstream weights are not available. Do not pass -f/--upstream_trainable."
             )
+        if self.training and torch.is_grad_enabled() and not self._warned_grad:
+            self._warned_grad = True
+            warnings.warn(
+                "s3prl_b200 upstream called in training mode with autograd enabled: it has no trainable parameters, "
+                "its outputs are constants for autograd (frozen upstream). Fine-tuning the upstream "
+                "(-f/--upstream_trainable) is not supported.",
+                RuntimeWarning,
+                stacklevel=2,
+            )
         wavs = [w.detach().to(torch.float32).contiguous() for w in wavs]
         lens = [int(w.numel()) for w in wavs]
         B = len(wavs)
@@ -180,17 +232,37 @@ class UpstreamExpert(nn.Module):
         if T < 1:
             raise ValueError(f"waveforms too short ({max_len} samples): the conv stack needs >= 400 samples")
         NL, D = self.arch.encoder_layers, self.arch.encoder_embed_dim
+        need_ffn = self.feature_selection == "fairseq_layers_before_residual" or bool(self.hooks)
+        need_last = self.arch.layer_norm_first and (self.feature_selection == "fairseq_layers" or bool(self.hooks))
         with torch.cuda.device(device):
             out = torch.empty((NL + 1, B, T, D), dtype=torch.float32, device=device)
+            ffn = torch.empty((NL, B, T, D), dtype=torch.float32, device=device) if need_ffn else None
+            last = torch.empty((B, T, D), dtype=torch.float32, device=device) if need_last else None
             ptrs = (C.c_void_p * B)(*[w.data_ptr() for w in wavs])
             lens_c = (C.c_int64 * B)(*lens)
+            opts = _lib.S3BForwardOpts(lanes=int(self.lanes))
+            if ffn is not None:
+                opts.ffn_out = ffn.data_ptr()
+            if last is not None:
+                opts.last_residual = last.data_ptr()
             _lib.check(
-                native.lib.s3b_forward(
+                native.lib.s3b_forward_ex(
                     native.handle, ptrs, lens_c, B, max_len, C.c_void_p(out.data_ptr()),
-                    C.c_void_p(torch.cuda.current_stream(device).cuda_stream),
+                    C.c_void_p(torch.cuda.current_stream(device).cuda_stream), C.byref(opts),
                 )
             )
         hidden_states = tuple(out[i] for i in range(NL + 1))
+        # layer outputs as the reference's layer_results[i][0]: identical to hidden state i+1 except that a pre-LN
+        # model's last entry is the stream BEFORE encoder.layer_norm (wav2vec2_model.py:3049-3050, 3095-3099)
+        layer_out = [out[i + 1] for i in range(NL)]
+        if last is not None:
+            layer_out[-1] = last
+        if self.feature_selection == "fairseq_layers":  # wav2vec2/expert.py:81-86
+            return {"hidden_states": layer_out}
+        if self.feature_selection == "fairseq_layers_before_residual":  # wav2vec2/expert.py:87-93
+            return {"hidden_states": [ffn[i] for i in range(NL)]}
+        if self.hooks:
+            return self._run_hooks(out, layer_out, ffn)
         result: Dict[str, Union[torch.Tensor, tuple]] = {
             "_hidden_states_info": tuple([f"self.model.encoder.layers[{i}]" for i in range(NL)] + ["self.model.encoder"]),
             "hidden_states": hidden_states,
@@ -200,9 +272,35 @@ class UpstreamExpert(nn.Module):
             result[f"hidden_state_{i}"] = h
         return result
 
-    def forward_host(self, wavs_host: List[torch.Tensor]) -> torch.Tensor:
-        """End-to-end from HOST buffers through ``s3b_forward_host`` (H2D and D2H inside the call).
-        Returns a pinned host tensor [NL+1, B, T, D]."""
+    def _run_hooks(self, out: torch.Tensor, layer_out: List[torch.Tensor], ffn: torch.Tensor) -> Dict:
+        """Custom ``hooks=`` (interfaces.py:74-131): every transform sees the (input, output) pair the reference's
+        forward hook on that module would see — time-major [T, B, D] tensors for the encoder layers
+        (wav2vec2_model.py:3260-3322 returns ``x, (attn, layer_result)``), batch-major for the encoder itself."""
+        NL = self.arch.encoder_layers
+        hiddens = []
+        for path, transform in self.hooks:
+            m_ = _LAYER_PATH.match(path)
+            if m_:
+                i = int(m_.group(1))
+                inp = (out[i].transpose(0, 1),)
+                outp = (layer_out[i].transpose(0, 1), (None, ffn[i].transpose(0, 1)))
+            else:  # TransformerEncoder.forward -> (x, layer_results) (wav2vec2_model.py:3046-3052)
+                inp = (None,)
+                results = [(layer_out[i].transpose(0, 1), None, ffn[i].transpose(0, 1)) for i in range(NL)]
+                outp = (out[NL], results)
+            hiddens.append((path, transform(inp, outp)))
+        if callable(self.hook_postprocess):
+            hiddens = self.hook_postprocess(hiddens)
+        names, hs = zip(*hiddens)
+        result = {"_hidden_states_info": names, "hidden_states": hs, "last_hidden_state": hs[-1]}
+        for i, h in enumerate(hs):
+            result[f"hidden_state_{i}"] = h
+        return result
+
+    def forward_host(self, wavs_host: List[torch.Tensor], keep_device: bool = False):
+        """End-to-end from HOST buffers through ``s3b_forward_host[_ex]`` (H2D and D2H inside the call).
+        Returns a pinned host tensor [NL+1, B, T, D]; with ``keep_device`` also the device-resident copy
+        (a torch tensor of the same shape) for device-side consumers such as the Featurizer."""
         native = self._ensure_native(self._device_anchor.device)
         wavs = [w.detach().to("cpu", torch.float32).contiguous() for w in wavs_host]
         lens = [int(w.numel()) for w in wavs]
@@ -218,6 +316,12 @@ class UpstreamExpert(nn.Module):
         ptrs = (C.c_void_p * B)(*[w.data_ptr() for w in wavs])
         lens_c = (C.c_int64 * B)(*lens)
         with torch.cuda.device(native.device):
+            if keep_device:
+                dev = torch.empty(shape, dtype=torch.float32, device=native.device)
+                torch.cuda.current_stream(native.device).synchronize()  # the call runs on the library's own streams
+                _lib.check(native.lib.s3b_forward_host_ex(native.handle, ptrs, lens_c, B, max_len,
+                                                          C.c_void_p(out.data_ptr()), C.c_void_p(dev.data_ptr())))
+                return out, dev
             _lib.check(native.lib.s3b_forward_host(native.handle, ptrs, lens_c, B, max_len, C.c_void_p(out.data_ptr())))
         return out
 

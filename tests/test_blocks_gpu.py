@@ -90,6 +90,11 @@ def test_layernorm(s3b_lib, D, gelu):
         (2, 200, 2, [200, 130]),
         (3, 499, 12, [499, 250, 1]),
         (2, 129, 4, [129, 65]),
+        # BASELINE C3 length (wav2vec2_large 20 s -> T = 999: 16 key blocks, V^T row stride Tp = 1000) and neighbours
+        (2, 999, 16, [999, 640]),
+        (2, 1000, 2, [1000, 961]),
+        (3, 1023, 2, [1023, 1, 513]),
+        (1, 1025, 1, [1025]),
     ],
 )
 def test_attention(s3b_lib, B, T, H, valid):

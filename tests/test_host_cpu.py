@@ -120,7 +120,9 @@ def test_header_is_plain_c_and_links(s3b_lib, tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, (r.stdout, r.stderr)
-    assert "23 entry points" in r.stdout and "49 3" in r.stdout
+    from s3prl_b200 import lib as L2
+
+    assert f"{len(L2.EXPORTED_SYMBOLS)} entry points" in r.stdout and "49 3" in r.stdout
 
 
 def test_hub_covers_the_same_skeleton_relatives():
@@ -189,3 +191,100 @@ def test_shard_and_gather_gloo_world2(tmp_path):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_converted_checkpoint_layouts_roundtrip(tmp_path):
+    """N4: every converted layout the reference's *_local entries read (hubert/convert.py:37-56,
+    wav2vec2/convert.py:26-39, wavlm/expert.py:37-40) is written by save_converted_checkpoint and read back by
+    load_reference_checkpoint into the same ArchConfig and tensors; a file with a missing key raises the reference's
+    ValueError text."""
+    from s3prl_b200 import hub
+    from s3prl_b200.upstream.configs import ARCHS
+    from s3prl_b200.upstream.convert import converted_checkpoint, save_converted_checkpoint
+    from s3prl_b200.upstream.weights import fabricate_state_dict, load_reference_checkpoint
+
+    for name in ("hubert_base", "wav2vec2_large_ll60k", "wavlm_base_plus", "unispeech_sat_base_plus", "wavlm_large"):
+        cfg = ARCHS[name]
+        sd = fabricate_state_dict(cfg, 0)
+        path = tmp_path / f"{name}.pt"
+        save_converted_checkpoint(path, cfg, sd)
+        got_cfg, got_sd = load_reference_checkpoint(str(path), cfg.family)
+        assert got_cfg == cfg, name
+        assert got_sd.keys() == sd.keys() and all(torch.equal(got_sd[k], sd[k]) for k in sd)
+        # the hub's *_local entry builds an expert from the file (no GPU needed until the first forward)
+        local = {"hubert": "hubert_local", "wav2vec2": "wav2vec2_local", "wavlm": "wavlm_local"}[cfg.family]
+        e = hub.ENTRIES[local](str(path))
+        assert e.arch == cfg and e.num_layers == cfg.encoder_layers
+    layout = converted_checkpoint(ARCHS["hubert_base"], {})
+    assert set(layout) == {"task_cfg", "model_cfg", "model_weight", "dictionaries_symbols"}
+    assert set(converted_checkpoint(ARCHS["wav2vec2_base_960"], {})) == {"task_cfg", "model_cfg", "model_weight"}
+    assert set(converted_checkpoint(ARCHS["wavlm_base"], {})) == {"cfg", "model"}
+    bad = tmp_path / "bad.pt"
+    torch.save({"model_cfg": {}, "model_weight": {}}, bad)
+    with pytest.raises(ValueError, match="required key: task_cfg is missing"):
+        load_reference_checkpoint(str(bad), "hubert")
+
+
+def test_fairseq_state_conversion():
+    """convert_fairseq_state == load_and_convert_fairseq_ckpt minus the I/O (hubert/convert.py:17-34,
+    wav2vec2/convert.py:14-23): cfg.task / cfg.model / model / dictionaries are re-keyed, nothing else."""
+    from s3prl_b200.upstream.configs import arch_from_reference_cfg
+    from s3prl_b200.upstream.convert import convert_fairseq_state
+
+    class Dictionary:  # stand-in for fairseq.data.dictionary.Dictionary (only .symbols is read)
+        def __init__(self, n):
+            self.symbols = [str(i) for i in range(n)]
+
+    w = {"layer_norm.weight": torch.ones(512)}
+    state = {"cfg": {"task": {"normalize": False, "label_rate": 50.0}, "model": {"encoder_layers": 12, "extractor_mode": "default"}},
+             "model": w, "task_state": {"dictionaries": [Dictionary(504)]}}
+    out = convert_fairseq_state(state, "hubert")
+    assert set(out) == {"task_cfg", "model_cfg", "model_weight", "dictionaries_symbols"}
+    assert out["model_weight"] is w and len(out["dictionaries_symbols"][0]) == 504
+    assert arch_from_reference_cfg("hubert", out["model_cfg"], out["task_cfg"]).encoder_layers == 12
+    out2 = convert_fairseq_state({"cfg": state["cfg"], "model": w}, "wav2vec2")
+    assert set(out2) == {"task_cfg", "model_cfg", "model_weight"}
+    with pytest.raises(ValueError):
+        convert_fairseq_state({"model": w}, "hubert")
+    with pytest.raises(ValueError):
+        convert_fairseq_state({"cfg": state["cfg"], "model": w}, "hubert")  # no dictionaries
+
+
+@pytest.mark.parametrize("kind,kw", [
+    ("hubert", {}),
+    ("hubert", dict(feat_extract_norm="layer", do_stable_layer_norm=True, conv_bias=True)),
+    ("wav2vec2", {}),
+    ("wavlm", {}),
+])
+def test_huggingface_second_oracle(kind, kw):
+    """N4: the HF -> fairseq parameter-name map (upstream/convert.py) against an INDEPENDENT implementation: a random
+    transformers Hubert/Wav2Vec2/WavLM model (the reference's hf_* experts run these, hf_hubert/expert.py:12-41)
+    evaluated by transformers' own forward must agree with oracle/upstream_oracle.py on the renamed weights
+    (equal-length batch: HF's "group-norm" models ignore the attention mask). Also pins WavLM's gated relative
+    position bias in the oracle against a second code base."""
+    transformers = pytest.importorskip("transformers")
+    import dataclasses
+
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import upstream_oracle as O
+    from s3prl_b200.upstream.convert import hf_to_fairseq_key, load_hf_model
+
+    Cfg = {"hubert": transformers.HubertConfig, "wav2vec2": transformers.Wav2Vec2Config, "wavlm": transformers.WavLMConfig}[kind]
+    Mod = {"hubert": transformers.HubertModel, "wav2vec2": transformers.Wav2Vec2Model, "wavlm": transformers.WavLMModel}[kind]
+    torch.manual_seed(0)
+    cfg = Cfg(num_hidden_layers=2, **kw)
+    cfg.layerdrop = 0.0
+    model = Mod(cfg).eval()
+    with torch.no_grad():
+        for _n, p in model.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    arch, sd = load_hf_model(model)
+    assert [k for k in model.state_dict() if hf_to_fairseq_key(k, arch.extractor_mode) is None] == ["masked_spec_embed"]
+    x = torch.randn(2, 6000)
+    with torch.no_grad():
+        hf = model(x, output_hidden_states=True).hidden_states
+        ref, _ = O.upstream_forward(list(x), {k: v.detach() for k, v in sd.items()}, dataclasses.replace(arch, normalize=False))
+    assert len(hf) == len(ref) == 3
+    for a, b in zip(hf, ref):
+        assert ((a - b).norm() / b.norm()).item() < 5e-6

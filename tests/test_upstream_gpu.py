@@ -52,13 +52,16 @@ def _compare(got, ref, what):
 from s3prl_b200.upstream.configs import ARCHS  # noqa: E402
 
 GOLDEN_MODELS = sorted(p.stem for p in GOLDEN.glob("*.pt") if p.stem in ARCHS)
+# BASELINE.json sizes on a batch the CPU reference affords (oracle/make_golden.py FULL_SIZE): wav2vec2_large at
+# T = 999 (C3, both variants), wavlm_base_plus at T = 499 incl. a ragged pair (C4)
+FULL_SIZE = sorted(p.stem for p in GOLDEN.glob("c[0-9]_*.pt"))
 
 
-@pytest.mark.parametrize("name", GOLDEN_MODELS)
+@pytest.mark.parametrize("name", GOLDEN_MODELS + FULL_SIZE)
 def test_matches_reference_golden(s3b_lib, name):
     fx = torch.load(GOLDEN / f"{name}.pt", weights_only=False)
-    expert = _expert(name)
-    cs = fx["channel_stride"]
+    expert = _expert(fx["arch"])
+    cs, ts = fx["channel_stride"], fx.get("time_stride", 1)
     worst = 0.0
     for case in fx["cases"]:
         wavs = [w.cuda() for w in _wavs(case["lens"], case["wav_seed"])]
@@ -68,7 +71,8 @@ def test_matches_reference_golden(s3b_lib, name):
         assert tuple(hs[0].shape) == tuple(case["shape"])
         assert res["last_hidden_state"] is hs[-1]
         for l, h in enumerate(hs):
-            worst = max(worst, _compare(h[:, :, ::cs].cpu(), case["sub"][l], f"{name} case lens={case['lens']} layer {l}"))
+            sub = h[:, (h.shape[1] - 1) % ts :: ts, ::cs]
+            worst = max(worst, _compare(sub.cpu(), case["sub"][l], f"{name} case lens={case['lens']} layer {l}"))
             nrm = h.double().norm().item()
             assert abs(nrm - case["norms"][l].item()) < REL_TOL * case["norms"][l].item()
     print(f"{name}: worst per-layer relative error vs reference golden = {worst:.3e}")
@@ -80,6 +84,7 @@ def test_matches_reference_golden(s3b_lib, name):
         ("hubert_base", [160000, 123457, 80000, 16000, 800]),  # the survey's ragged parity set
         ("hubert_base", [32000, 32000, 32000]),                # no padding
         ("wav2vec2_base_960", [48000, 31999, 1200]),
+        ("wav2vec2_base_960", [16000, 50, 399, 5]),  # shorter than the receptive field: the reference's mask index wraps
         ("wavlm_base_plus", [40000, 33333, 900]),
     ],
 )
@@ -143,3 +148,92 @@ def test_short_utterances(s3b_lib):
         hs = expert([w.cuda() for w in wavs])["hidden_states"]
         for l, (h, r) in enumerate(zip(hs, ref)):
             _compare(h.cpu(), r, f"short lens={lens} layer {l}")
+
+
+def test_lanes_are_bit_identical(s3b_lib):
+    """Two utterance micro-batches on two streams (the default) == one lane, bit for bit, also for odd / ragged batches."""
+    expert = _expert("hubert_base")
+    for lens in ([32000] * 4, [24000, 17000, 9000, 16000, 800], [16000, 12000]):
+        wavs = [w.cuda() for w in _wavs(lens, seed=77)]
+        outs = []
+        for lanes in (1, 2):
+            expert.lanes = lanes
+            try:
+                outs.append(torch.stack(expert(wavs)["hidden_states"]).clone())
+            finally:
+                expert.lanes = 0
+        assert torch.equal(outs[0], outs[1]), lens
+        assert torch.equal(torch.stack(expert(wavs)["hidden_states"]), outs[0])
+
+
+def test_wav2vec2_feature_selection_and_hooks(s3b_lib):
+    """feature_selection of the wav2vec2 expert (wav2vec2/expert.py:35-39,81-93) and custom UpstreamBase hooks
+    (interfaces.py:74-131) against the oracle: layer outputs, fc2 outputs before the residual add."""
+    import torch.nn.functional as F
+    import upstream_oracle as O
+    from s3prl_b200.upstream.configs import ARCHS
+    from s3prl_b200.upstream.expert import UpstreamExpert
+    from s3prl_b200.upstream.weights import fabricate_state_dict
+
+    for name in ("wav2vec2_base_960", "wav2vec2_large_ll60k"):
+        cfg = ARCHS[name]
+        sd = fabricate_state_dict(cfg, seed=0)
+        wavs = _wavs([9000, 6000], seed=21)
+        with torch.no_grad():
+            ref, pad = O.upstream_forward(wavs, sd, cfg)
+        NL = cfg.encoder_layers
+        _EXPERTS.clear()
+        fl = UpstreamExpert(name=name, seed=0, feature_selection="fairseq_layers").to("cuda")
+        got = fl([w.cuda() for w in wavs])["hidden_states"]
+        assert len(got) == NL
+        for l in range(NL - 1):
+            _compare(got[l].cpu(), ref[l + 1], f"{name} fairseq_layers {l}")
+        if cfg.layer_norm_first:  # last entry is the stream BEFORE encoder.layer_norm
+            ln = F.layer_norm(got[-1].cpu(), (got[-1].shape[-1],), sd["encoder.layer_norm.weight"],
+                              sd["encoder.layer_norm.bias"], 1e-5)
+            _compare(ln, ref[NL], f"{name} fairseq_layers last (re-normalised)")
+        else:
+            _compare(got[-1].cpu(), ref[NL], f"{name} fairseq_layers last")
+        del fl
+        br = UpstreamExpert(name=name, seed=0, feature_selection="fairseq_layers_before_residual").to("cuda")
+        pre = br([w.cuda() for w in wavs])["hidden_states"]
+        assert len(pre) == NL
+        if cfg.layer_norm_first:  # residual stream: h_{l+1} = r + fc2_out, r = h_l + attention(...): check the last step
+            hk = UpstreamExpert(
+                name=name, seed=0,
+                hooks=[(f"self.model.encoder.layers[{NL - 2}]", lambda i, o: (o[0] - o[1][1]).transpose(0, 1))],
+            ).to("cuda")
+            r = hk([w.cuda() for w in wavs])["hidden_states"][0]
+            _compare((r + pre[NL - 2]).cpu(), ref[NL - 1], f"{name} r + fc2 == hidden state")
+            del hk
+        else:  # post-LN: h_{l+1} = LN2(x1 + fc2_out) with x1 = LN1(h_l + attn): verify through the oracle pieces
+            p = f"encoder.layers.{NL - 1}"
+            h = ref[NL - 1]
+            a = O.self_attention(h, {k: v.float() for k, v in sd.items()}, f"{p}.self_attn", cfg.encoder_attention_heads, pad)
+            x1 = F.layer_norm(h + a, (h.shape[-1],), sd[f"{p}.self_attn_layer_norm.weight"], sd[f"{p}.self_attn_layer_norm.bias"], 1e-5)
+            f2 = F.linear(F.gelu(F.linear(x1, sd[f"{p}.fc1.weight"], sd[f"{p}.fc1.bias"])), sd[f"{p}.fc2.weight"], sd[f"{p}.fc2.bias"])
+            _compare(pre[NL - 1].cpu(), f2, f"{name} fairseq_layers_before_residual last")
+        del br
+    with pytest.raises(TypeError):
+        UpstreamExpert(name="hubert_base", feature_selection="fairseq_layers")
+    with pytest.raises(ValueError):
+        UpstreamExpert(name="hubert_base", hooks=[("self.model.feature_extractor", lambda i, o: o)])
+
+
+def test_local_checkpoint_entries(s3b_lib, tmp_path):
+    """*_local hub entries read a converted reference checkpoint of each layout (hubert/convert.py:37-56,
+    wav2vec2/convert.py:26-39, wavlm/expert.py:37-40) and reproduce the named entry bit for bit."""
+    from s3prl_b200 import hub
+    from s3prl_b200.upstream.configs import ARCHS
+    from s3prl_b200.upstream.convert import save_converted_checkpoint
+    from s3prl_b200.upstream.weights import fabricate_state_dict
+
+    wavs = [w.cuda() for w in _wavs([12000, 7001], seed=3)]
+    for name, local in (("hubert_base", "hubert_local"), ("wav2vec2_base_960", "wav2vec2_local"),
+                        ("wavlm_base_plus", "wavlm_local"), ("unispeech_sat_base_plus", "unispeech_sat_local")):
+        path = tmp_path / f"{name}.pt"
+        save_converted_checkpoint(path, ARCHS[name], fabricate_state_dict(ARCHS[name], 0))
+        _EXPERTS.clear()
+        a = torch.stack(hub.ENTRIES[name]().to("cuda")(wavs)["hidden_states"])
+        b = torch.stack(hub.ENTRIES[local](str(path)).to("cuda")(wavs)["hidden_states"])
+        assert torch.equal(a, b), name
