@@ -22,7 +22,9 @@ int main(void) {
         (const void*)s3b_weighted_sum_backward, (const void*)s3b_fbank,    (const void*)s3b_fbank_num_frames,
         (const void*)s3b_trimmed_lengths, (const void*)s3b_melspec,        (const void*)s3b_linear_f32,
         (const void*)s3b_layernorm_f32,  (const void*)s3b_attention_f32,  (const void*)s3b_forward_ex,
-        (const void*)s3b_forward_host_ex, (const void*)s3b_wavlm_buckets,
+        (const void*)s3b_forward_host_ex, (const void*)s3b_wavlm_buckets, (const void*)s3b_peer_create,
+        (const void*)s3b_peer_connect,   (const void*)s3b_peer_slot,       (const void*)s3b_peer_push,
+        (const void*)s3b_peer_wait,      (const void*)s3b_peer_destroy,
     };
     s3b_config cfg;
     int64_t lens[2] = {16000, 800};

@@ -133,6 +133,27 @@ int s3b_weighted_sum(const float* hs, int32_t num, int64_t n_per_layer, const fl
 int s3b_weighted_sum_backward(const float* hs, int32_t num, int64_t n_per_layer, const float* grad_out,
                               float* grad_w, void* stream);
 
+/* Fused Featurizer + all-gather over NVLink peer memory (multi-GPU step) ---------------------------
+ * One process per GPU on one NVSwitch node. Every rank creates an exchange object (the library cudaMalloc's
+ * [slots][world][block_elems] floats + flags and exports them as a 64-byte CUDA IPC handle), the host side exchanges
+ * the handles (torch.distributed.all_gather in s3prl_b200/parallel.py) and calls s3b_peer_connect with all of them.
+ *  s3b_peer_push(step): ONE kernel computes sum_l w[l] * hs[l][i] over this rank's block (hs layers layer_stride
+ *    elements apart) and stores it into slot step % slots of EVERY rank's buffer at this rank's position, then
+ *    releases a per-(slot, rank) flag = step + 1 at system scope.
+ *  s3b_peer_wait(step): stream-ordered wait until every rank's flag of that slot has reached step + 1: the local
+ *    gathered buffer s3b_peer_slot(step) = [world][block_elems] is then complete.
+ * Contract: a slot is rewritten `slots` steps later; the host protocol (parallel.FeatureGatherer) waits for step s-1
+ * before pushing step s, so a writer never overtakes a reader by more than slots - 2 steps. */
+typedef struct s3b_peer s3b_peer;
+int s3b_peer_create(int32_t rank, int32_t world, int64_t block_elems, int32_t slots, s3b_peer** out,
+                    void* ipc_handle_out /* 64 bytes */);
+int s3b_peer_connect(s3b_peer* p, const void* all_handles /* world x 64 bytes, rank-major */);
+float* s3b_peer_slot(s3b_peer* p, uint32_t step);
+int s3b_peer_push(s3b_peer* p, const float* hs, int32_t num, int64_t layer_stride, const float* w, uint32_t step,
+                  void* stream);
+int s3b_peer_wait(s3b_peer* p, uint32_t step, void* stream);
+void s3b_peer_destroy(s3b_peer* p);
+
 /* fbank baseline upstream (s3prl/upstream/baseline/expert.py:69-79 over torchaudio.compliance.kaldi.fbank,
  * fbank.yaml: 80 mel bins, 25 ms / 10 ms, log; + 2 x ComputeDeltas(5) + per-utterance CMVN).
  *  wavs : host array of `batch` DEVICE pointers (fp32, un-padded), lens : host array of lengths

@@ -25,6 +25,7 @@ import torch
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "oracle"))
 GOLDEN = ROOT / "tests" / "golden"
 
 from s3prl_b200.upstream.configs import ARCHS, CONV_LAYERS  # noqa: E402
@@ -58,81 +59,7 @@ def seeded_wavs(lens, seed):
     return [torch.randn(n, generator=g) for n in lens]
 
 
-def reference_expert(name: str, sd):
-    """Instantiate the reference's UpstreamExpert on a fabricated checkpoint."""
-    cfg = ARCHS[name]
-    model_cfg = dict(
-        extractor_mode=cfg.extractor_mode,
-        conv_bias=cfg.conv_bias,
-        layer_norm_first=cfg.layer_norm_first,
-        encoder_layers=cfg.encoder_layers,
-        encoder_embed_dim=cfg.encoder_embed_dim,
-        encoder_ffn_embed_dim=cfg.encoder_ffn_embed_dim,
-        encoder_attention_heads=cfg.encoder_attention_heads,
-        conv_feature_layers=str(CONV_LAYERS),
-        conv_pos=cfg.conv_pos,
-        conv_pos_groups=cfg.conv_pos_groups,
-        activation_fn="gelu",
-        dropout=0.1,
-        attention_dropout=0.1,
-        encoder_layerdrop=0.05,
-    )
-    tmp = tempfile.NamedTemporaryFile(suffix=".pt", delete=False)
-    tmp.close()
-    try:
-        if cfg.family == "hubert":
-            from s3prl.upstream.hubert.expert import UpstreamExpert
-            from s3prl.upstream.hubert.hubert_model import HubertConfig, HubertModel, HubertPretrainingConfig
-            from s3prl.upstream.utils import merge_with_parent
-
-            model_cfg.update(label_rate=50.0, final_dim=256, untie_final_proj=True)
-            task_cfg = dict(normalize=cfg.normalize, sample_rate=16000, label_rate=50.0)
-            symbols = [[str(i) for i in range(504)]]
-            skeleton = HubertModel(
-                merge_with_parent(HubertConfig, model_cfg), merge_with_parent(HubertPretrainingConfig, task_cfg), symbols
-            )
-            full = skeleton.state_dict()
-            full.update(sd)
-            torch.save(
-                {"task_cfg": task_cfg, "model_cfg": model_cfg, "model_weight": full, "dictionaries_symbols": symbols},
-                tmp.name,
-            )
-        elif cfg.family == "wav2vec2":
-            from s3prl.upstream.utils import merge_with_parent
-            from s3prl.upstream.wav2vec2.expert import UpstreamExpert
-            from s3prl.upstream.wav2vec2.wav2vec2_model import Wav2Vec2Config, Wav2Vec2Model
-
-            model_cfg.update(quantize_targets=True, final_dim=768 if cfg.encoder_embed_dim == 1024 else 256)
-            task_cfg = dict(normalize=cfg.normalize, sample_rate=16000)
-            skeleton = Wav2Vec2Model(merge_with_parent(Wav2Vec2Config, model_cfg))
-            full = skeleton.state_dict()
-            full.update(sd)
-            torch.save({"task_cfg": task_cfg, "model_cfg": model_cfg, "model_weight": full}, tmp.name)
-        else:
-            if name.startswith("unispeech_sat"):
-                from s3prl.upstream.unispeech_sat.expert import UpstreamExpert
-            else:
-                from s3prl.upstream.wavlm.expert import UpstreamExpert
-            from s3prl.upstream.wavlm.WavLM import WavLM, WavLMConfig
-
-            model_cfg.update(
-                normalize=cfg.normalize,
-                relative_position_embedding=cfg.relative_position_embedding,
-                num_buckets=cfg.num_buckets,
-                max_distance=cfg.max_distance,
-                gru_rel_pos=cfg.gru_rel_pos,
-            )
-            skeleton = WavLM(WavLMConfig(model_cfg))
-            full = skeleton.state_dict()
-            full.update(sd)
-            torch.save({"cfg": model_cfg, "model": full}, tmp.name)
-        missing = set(sd) - set(skeleton.state_dict())
-        assert not missing, f"fabricated keys unknown to the reference model: {sorted(missing)[:5]}"
-        expert = UpstreamExpert(tmp.name)
-    finally:
-        os.unlink(tmp.name)
-    expert.eval()
-    return expert
+from ref_runtime import reference_expert  # noqa: E402  (the reference itself on a fabricated checkpoint)
 
 
 def make_model_fixture(name: str, fixture: str = None):

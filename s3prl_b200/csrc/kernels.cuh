@@ -34,6 +34,12 @@ cudaError_t launch_weighted_sum(const float* hs, int NL, size_t n_per_layer, con
 cudaError_t launch_weighted_sum_bwd(const float* hs, int NL, size_t n_per_layer, const float* gout, float* grad_w,
                                     cudaStream_t s);
 
+// ---- peer.cu: fused weighted sum + push all-gather over peer memory --------------------------------------------------
+cudaError_t launch_weighted_sum_push(const float* hs, int NL, size_t n_per_layer, size_t layer_stride, const float* w,
+                                     float* const* peer_dst, uint32_t* const* peer_flag, int n_peers, uint32_t seq,
+                                     unsigned int* counter, cudaStream_t s);
+cudaError_t launch_wait_flags(const uint32_t* flags, int n, uint32_t seq, cudaStream_t s);
+
 // ---- attention.cu --------------------------------------------------------------------------------
 struct AttnParams {
     CUtensorMap q_hi, q_lo;    // [B*H][T][64]  box {64, 128, 1}

@@ -1346,6 +1346,106 @@ extern "C" int s3b_weighted_sum_backward(const float* hs, int32_t num, int64_t n
 }
 
 // ------------------------------------------------------------------------------------------------
+// peer-memory feature exchange (fused weighted sum + all-gather, csrc/peer.cu)
+// ------------------------------------------------------------------------------------------------
+struct s3b_peer {
+    int rank = 0, world = 1, slots = 3;
+    int64_t block = 0;       // floats per rank block
+    void* base = nullptr;    // own allocation: [slots][world][block] floats | flags [slots][world] u32 | counter
+    size_t bytes = 0, flags_off = 0, counter_off = 0;
+    std::vector<void*> peer_base;  // every rank's allocation as mapped in THIS process (own: base)
+    bool connected = false;
+};
+
+extern "C" int s3b_peer_create(int32_t rank, int32_t world, int64_t block_elems, int32_t slots, s3b_peer** out,
+                               void* ipc_handle_out) {
+    if (!out || !ipc_handle_out) return fail("null argument");
+    if (world < 1 || world > 16 || rank < 0 || rank >= world) return fail("bad rank / world (max 16 ranks)");
+    if (block_elems < 4 || (block_elems & 3) != 0) return fail("block_elems must be a positive multiple of 4");
+    if (slots < 2 || slots > 8) return fail("slots must be in [2, 8]");
+    if (s3b_device_count() == 0) return fail("no CUDA device: s3prl_b200 has no CPU fallback");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    s3b_peer* p = new s3b_peer();
+    p->rank = rank, p->world = world, p->slots = slots, p->block = block_elems;
+    const size_t data = (size_t)slots * world * (size_t)block_elems * 4;
+    p->flags_off = (data + 255) & ~(size_t)255;
+    p->counter_off = p->flags_off + (((size_t)slots * world * 4 + 255) & ~(size_t)255);
+    p->bytes = p->counter_off + 256;
+    cudaError_t e = cudaMalloc(&p->base, p->bytes);
+    if (e == cudaSuccess) e = cudaMemset(p->base, 0, p->bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p->base);
+    if (e != cudaSuccess) {
+        if (p->base) cudaFree(p->base);
+        delete p;
+        return fail("peer buffer allocation / IPC export failed: %s", cudaGetErrorString(e));
+    }
+    memcpy(ipc_handle_out, &h, sizeof(h));
+    p->peer_base.assign(world, nullptr);
+    p->peer_base[rank] = p->base;
+    *out = p;
+    return 0;
+}
+
+extern "C" int s3b_peer_connect(s3b_peer* p, const void* all_handles) {
+    if (!p || !all_handles) return fail("null argument");
+    if (p->connected) return 0;
+    const cudaIpcMemHandle_t* hs = static_cast<const cudaIpcMemHandle_t*>(all_handles);
+    for (int r = 0; r < p->world; ++r) {
+        if (r == p->rank) continue;
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, hs[r], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail("cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+        }
+        p->peer_base[r] = ptr;
+    }
+    p->connected = true;
+    return 0;
+}
+
+extern "C" float* s3b_peer_slot(s3b_peer* p, uint32_t step) {
+    if (!p) return nullptr;
+    return static_cast<float*>(p->base) + (size_t)(step % p->slots) * p->world * (size_t)p->block;
+}
+
+extern "C" int s3b_peer_push(s3b_peer* p, const float* hs, int32_t num, int64_t layer_stride, const float* w,
+                             uint32_t step, void* stream) {
+    if (!p || !hs || !w) return fail("null argument");
+    if (!p->connected && p->world > 1) return fail("s3b_peer_connect has not been called");
+    const int slot = (int)(step % p->slots);
+    float* dst[16];
+    uint32_t* flag[16];
+    for (int r = 0; r < p->world; ++r) {
+        char* b = static_cast<char*>(p->peer_base[r]);
+        dst[r] = reinterpret_cast<float*>(b) + ((size_t)slot * p->world + p->rank) * (size_t)p->block;
+        flag[r] = reinterpret_cast<uint32_t*>(b + p->flags_off) + (size_t)slot * p->world + p->rank;
+    }
+    unsigned int* counter = reinterpret_cast<unsigned int*>(static_cast<char*>(p->base) + p->counter_off);
+    CUDA_OK(launch_weighted_sum_push(hs, num, (size_t)p->block, (size_t)layer_stride, w, dst, flag, p->world, step + 1,
+                                     counter, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int s3b_peer_wait(s3b_peer* p, uint32_t step, void* stream) {
+    if (!p) return fail("null argument");
+    const uint32_t* flags = reinterpret_cast<const uint32_t*>(static_cast<char*>(p->base) + p->flags_off) +
+                            (size_t)(step % p->slots) * p->world;
+    CUDA_OK(launch_wait_flags(flags, p->world, step + 1, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" void s3b_peer_destroy(s3b_peer* p) {
+    if (!p) return;
+    for (int r = 0; r < p->world; ++r)
+        if (r != p->rank && p->peer_base[r]) cudaIpcCloseMemHandle(p->peer_base[r]);
+    if (p->base) cudaFree(p->base);
+    delete p;
+}
+
+// ------------------------------------------------------------------------------------------------
 // building blocks for parity tests
 // ------------------------------------------------------------------------------------------------
 static int device_sm_count(int* out) {

@@ -30,6 +30,12 @@ EXPORTED_SYMBOLS = [
     "s3b_forward_ex",
     "s3b_forward_host_ex",
     "s3b_wavlm_buckets",
+    "s3b_peer_create",
+    "s3b_peer_connect",
+    "s3b_peer_slot",
+    "s3b_peer_push",
+    "s3b_peer_wait",
+    "s3b_peer_destroy",
     "s3b_profile_enable",
     "s3b_profile_read",
     "s3b_launch_count",
@@ -127,6 +133,14 @@ def load() -> C.CDLL:
     lib.s3b_forward_ex.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i32, i64, f32p, vp, C.POINTER(S3BForwardOpts)]
     lib.s3b_forward_host_ex.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i32, i64, f32p, f32p]
     lib.s3b_wavlm_buckets.argtypes = [i32, i32, C.POINTER(i32), i32, C.POINTER(i32)]
+    lib.s3b_peer_create.argtypes = [i32, i32, i64, i32, C.POINTER(vp), vp]
+    lib.s3b_peer_connect.argtypes = [vp, vp]
+    lib.s3b_peer_slot.argtypes = [vp, C.c_uint32]
+    lib.s3b_peer_slot.restype = vp
+    lib.s3b_peer_push.argtypes = [vp, f32p, i32, i64, f32p, C.c_uint32, vp]
+    lib.s3b_peer_wait.argtypes = [vp, C.c_uint32, vp]
+    lib.s3b_peer_destroy.argtypes = [vp]
+    lib.s3b_peer_destroy.restype = None
     lib.s3b_profile_enable.argtypes = [vp, i32]
     lib.s3b_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64), i32]
     lib.s3b_launch_count.argtypes = [vp]

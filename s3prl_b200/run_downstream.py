@@ -130,9 +130,74 @@ def reject_unsupported(argv) -> None:
 
 
 def main():
-    reject_unsupported(sys.argv[1:])
-    names = inject()
+    """Extra flags (consumed here, never seen by the reference's parser):
+      --synthetic_data   replace the CTC expert's dataloaders by LibriSpeech-shaped synthetic batches (s3prl_b200/synthetic.py;
+                         no corpus and no audio I/O exist in this image)
+      --stage_timing     CUDA-event timers around the upstream / featurizer / downstream forwards; one JSON line
+                         ("s3b_stage_timing") on stderr at exit
+    Under torchrun the reference expects ``--local_rank`` (run_downstream.py:29,166-168); it is added from LOCAL_RANK."""
+    import json
+    import os
+
+    argv = sys.argv[1:]
+    synthetic = "--synthetic_data" in argv
+    timing = "--stage_timing" in argv
+    argv = [a for a in argv if a not in ("--synthetic_data", "--stage_timing")]
+    reject_unsupported(argv)
+    if "LOCAL_RANK" in os.environ and "--local_rank" not in argv and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        argv += ["--local_rank", os.environ["LOCAL_RANK"]]
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    sys.argv = [sys.argv[0]] + argv
+    if os.environ.get("S3B_NO_INJECT"):  # plumbing tests on a GPU-less host: the reference's own upstreams
+        install_shims()
+        names = []
+    else:
+        names = inject()
     print(f"[s3prl_b200] injected {len(names)} B200-native entries into s3prl.hub", file=sys.stderr)
+    import s3prl
+
+    # configs and vocabularies are addressed relative to the s3prl package directory (run_downstream.py:138-139,
+    # ctc/librispeech.yaml:51): run from there, like `cd s3prl; python run_downstream.py ...`
+    pkg_dir = os.path.dirname(os.path.abspath(s3prl.__file__))
+    if "-o" in argv or "--override" in argv or True:
+        for flag in ("-p", "--expdir"):
+            if flag in argv:  # keep a user-given relative expdir relative to the original cwd
+                i = argv.index(flag) + 1
+                argv[i] = os.path.abspath(argv[i])
+        sys.argv = [sys.argv[0]] + argv
+    os.chdir(pkg_dir)
+    if synthetic:
+        import s3prl.downstream.ctc.expert as ctc_expert
+
+        from . import synthetic as syn
+
+        syn.install(ctc_expert)
+        print("[s3prl_b200] CTC dataloaders replaced by synthetic LibriSpeech-shaped batches", file=sys.stderr)
+    timer = None
+    if timing:
+        import atexit
+
+        import s3prl.downstream.ctc.expert as ctc_expert
+
+        from .synthetic import StageTimer
+        from .upstream.expert import UpstreamExpert
+        from .upstream.featurizer import Featurizer
+
+        timer = StageTimer()
+        timer.wrap(UpstreamExpert, "upstream")
+        timer.wrap(Featurizer, "featurizer")
+        timer.wrap(ctc_expert.DownstreamExpert, "downstream")
+
+        def report():
+            try:
+                rec = timer.summary()
+                rec["rank"] = int(os.environ.get("RANK", "0"))
+                rec["world"] = int(os.environ.get("WORLD_SIZE", "1"))
+                print("s3b_stage_timing " + json.dumps(rec), file=sys.stderr, flush=True)
+            except Exception as e:  # never mask the run's own exit status
+                print(f"s3b_stage_timing failed: {e}", file=sys.stderr)
+
+        atexit.register(report)
     from s3prl import run_downstream
 
     run_downstream.main()

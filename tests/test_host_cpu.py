@@ -288,3 +288,60 @@ def test_huggingface_second_oracle(kind, kw):
     assert len(hf) == len(ref) == 3
     for a, b in zip(hf, ref):
         assert ((a - b).norm() / b.norm()).item() < 5e-6
+
+
+def _reference_install():
+    for cand in (REFERENCE, ROOT / "oracle" / "_ref"):
+        if (cand / "s3prl" / "downstream" / "runner.py").exists():
+            return cand
+    return None
+
+
+@pytest.mark.skipif(_reference_install() is None, reason="reference neither at /root/reference nor installed in oracle/_ref")
+def test_launcher_runs_reference_runner_on_synthetic_librispeech(tmp_path):
+    """BASELINE config 5 plumbing without a GPU: the launcher's synthetic LibriSpeech-shaped dataloader
+    (s3prl_b200/synthetic.py, replacing ctc/data.py:73-86 load_dataset) drives the reference's UNMODIFIED Runner.train
+    (runner.py:227-429) and CTC DownstreamExpert for one optimisation step; S3B_NO_INJECT keeps the reference's own CPU
+    fbank upstream so that the test needs no device. -f/--upstream_trainable is refused."""
+    import subprocess
+
+    env = dict(os.environ, PYTHONPATH=f"{ROOT}:{_reference_install()}", S3B_NO_INJECT="1")
+    cmd = [sys.executable, "-m", "s3prl_b200.run_downstream", "--synthetic_data", "-m", "train", "-u", "fbank", "-d", "ctc",
+           "-c", "downstream/ctc/librispeech.yaml", "-p", str(tmp_path / "exp"), "--device", "cpu", "-o",
+           "config.runner.total_steps=1,,config.runner.eval_step=100000,,config.runner.save_step=100000,,"
+           "config.runner.log_step=1,,config.downstream_expert.corpus.batch_size=2,,"
+           "config.downstream_expert.model.RNNs.dim=[64,64,64],,config.downstream_expert.model.project_dim=64"]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, cwd=str(tmp_path), timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert "train loss:" in r.stdout and "synthetic LibriSpeech-shaped" in r.stderr
+    r2 = subprocess.run(cmd[:3] + ["-f"] + cmd[3:], capture_output=True, text=True, env=env, cwd=str(tmp_path), timeout=300)
+    assert r2.returncode != 0 and "upstream_trainable is not supported" in r2.stderr
+
+
+def test_synthetic_batches_follow_collect_audio_batch_rules():
+    """Host batch assembly (ctc/data.py:11-43): descending length inside a batch, bucket halved when the first
+    utterance exceeds 300 000 samples, float32 waveforms, integer label arrays."""
+    import numpy as np
+
+    from s3prl_b200 import synthetic as syn
+
+    class Tok:
+        vocab_size = 31
+
+    dl = syn.load_dataset("train", Tok(), {"batch_size": 32, "bucketing": True, "num_workers": 0})
+    seen_half = seen_full = False
+    for i, (wavs, labels, files) in enumerate(dl):
+        lens = [len(w) for w in wavs]
+        assert lens == sorted(lens, reverse=True)
+        assert all(w.dtype == np.float32 for w in wavs) and all(l.dtype == np.int64 for l in labels)
+        assert len(wavs) == len(labels) == len(files)
+        if len(wavs) == 16:
+            seen_half = True
+            assert max(lens) <= 24 * 16000
+        if len(wavs) == 32:
+            seen_full = True
+            assert max(lens) <= 300000 and min(lens) >= 2 * 16000
+        assert len(wavs) in (16, 32)
+        if i > 200:
+            break
+    assert seen_full and seen_half

@@ -18,9 +18,11 @@ ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--warmup", type=int, default=1)
 ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--seconds", type=float, default=10.0)
+ap.add_argument("--lanes", type=int, default=0)
 args = ap.parse_args()
 
 expert = UpstreamExpert(name=args.model, seed=0).to("cuda")
+expert.lanes = args.lanes
 g = torch.Generator().manual_seed(0)
 wavs = [torch.randn(int(args.seconds * 16000), generator=g).cuda() for _ in range(args.batch)]
 w = torch.softmax(torch.zeros(expert.num_layers + 1, device="cuda"), -1)
