@@ -8,6 +8,7 @@ is compared with the exact fp32 oracle (relative Frobenius error per layer).
   fp16x2   : A = A_hi + A_lo (fp16), W rounded ONCE to fp16, products A_hi*W_hi + A_lo*W_hi           (2 MMAs)
   bf16x3f8 : bf16 hi*hi + the two correction products with e4m3 operands (4-bit significands)       (2 MMA units)
   fp16x2f8 : fp16x2 + the dropped A_hi*W_lo product with e4m3 operands                               (2.5 MMA units)
+  fp16f8x2 : fp16 hi*hi + BOTH first-order corrections (A_lo*W, A*W_lo) with e4m3 operands               (2 MMA units)
   tf32     : both operands rounded to 11-bit significands                                             (2 MMA units)
 
     python oracle/numerics_emulation.py [--models hubert_base wav2vec2_large_ll60k ...] [--seconds 2]
@@ -67,6 +68,11 @@ def contraction(scheme: str, a: torch.Tensor, w: torch.Tensor, op):
         al, wl = _fp16(a - ah), _fp16(w - wh)
         q = lambda t: _round_sig(t, 4)
         return op(ah, wh) + op(al, wh) + op(q(ah), q(wl))
+    if scheme == "fp16f8x2":
+        ah, wh = _fp16(a), _fp16(w)
+        al, wl = a - ah, w - wh
+        q = lambda t: _round_sig(t, 4)
+        return op(ah, wh) + op(q(al), q(wh)) + op(q(ah), q(wl))
     if scheme == "tf32":
         return op(_round_sig(a, 11), _round_sig(w, 11))
     raise ValueError(scheme)

@@ -56,6 +56,20 @@ struct GemmParams {
     float q_scale;
     __nv_bfloat16 *q_hi, *q_lo, *k_hi, *k_lo, *vt_hi, *vt_lo;
 
+    // ---- optional fused LayerNorm over the whole output row (CTA-pair kernel, N == ldo == 128 * ln_v4) ------------
+    // The n-tiles of a 128-row block are finished by different CTAs; each counts itself in on ln_counter[row block]
+    // after its stores, and the LAST one to arrive normalises the 128 complete rows of out_f32 (re-read from L2):
+    //   y = LayerNorm(out_f32 row) * ln_gamma + ln_beta (eps 1e-5), optional GELU -> ln_out_f32 / ln_out_hi,lo
+    // The values are the ones the separate layernorm_kernel would produce, bit for bit (same per-row arithmetic), and
+    // the LayerNorm traffic overlaps the MMAs of the CTA's next tile instead of running as its own HBM-bound kernel.
+    const float* ln_gamma;  // null = no fused LayerNorm
+    const float* ln_beta;
+    int ln_gelu;
+    float* ln_out_f32;
+    __nv_bfloat16* ln_out_hi;
+    __nv_bfloat16* ln_out_lo;
+    unsigned int* ln_counter;  // [batches * tiles_m_per_batch], zero on entry, left zero
+
     double alg_flops;  // host-side accounting only: 2*M*N*K with the un-padded K
 
     // CTA-pair kernel: 16-wide MMA k-steps issued per 64-wide k-block (0 = all 4). pos_conv with 48 channels per group

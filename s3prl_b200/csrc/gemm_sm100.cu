@@ -249,6 +249,68 @@ __device__ __forceinline__ void epi_chunk_coalesced(const GemmParams& p, const E
     __syncwarp();  // the staging buffer is rewritten by the next chunk
 }
 
+// One warp normalises one complete output row (fused LayerNorm of the CTA-pair kernel). Same arithmetic, in the same
+// order, as layernorm_kernel (norm.cu): two-pass statistics held in registers, biased variance, eps 1e-5.
+template <int V4>
+__device__ __forceinline__ void ln_row(const GemmParams& p, size_t row, int lane) {
+    constexpr int D = V4 * 128;
+    const float4* xr = reinterpret_cast<const float4*>(p.out_f32 + row * D);
+    float4 v[V4];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+        v[i] = __ldcg(xr + lane + 32 * i);  // written by other SMs a moment ago: read through L2
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+    const float4* g4 = reinterpret_cast<const float4*>(p.ln_gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(p.ln_beta);
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+        const int c4 = lane + 32 * i;
+        const float4 g = __ldg(g4 + c4), b = __ldg(b4 + c4);
+        float4 y;
+        y.x = (v[i].x - mean) * rstd * g.x + b.x;
+        y.y = (v[i].y - mean) * rstd * g.y + b.y;
+        y.z = (v[i].z - mean) * rstd * g.z + b.z;
+        y.w = (v[i].w - mean) * rstd * g.w + b.w;
+        if (p.ln_gelu) y.x = gelu_erf(y.x), y.y = gelu_erf(y.y), y.z = gelu_erf(y.z), y.w = gelu_erf(y.w);
+        if (p.ln_out_f32 != nullptr) reinterpret_cast<float4*>(p.ln_out_f32 + row * D)[c4] = y;
+        if (p.ln_out_hi != nullptr) {
+            uint32_t h0, l0, h1, l1;
+            split_pack2(y.x, y.y, h0, l0);
+            split_pack2(y.z, y.w, h1, l1);
+            reinterpret_cast<uint2*>(p.ln_out_hi + row * D)[c4] = make_uint2(h0, h1);
+            reinterpret_cast<uint2*>(p.ln_out_lo + row * D)[c4] = make_uint2(l0, l1);
+        }
+    }
+}
+
+// 16 of the 128 rows of a finished row block per epilogue warp. Not inlined: its registers (up to 40 for the row) must
+// not push the hot epilogue loop of the GEMM kernel into spills.
+__device__ __noinline__ void ln_tile_rows(const GemmParams* pp, int batch, int row0, int ewarp, int lane) {
+    const GemmParams& p = *pp;
+    const int r_begin = ewarp * 16;
+    for (int r = r_begin; r < r_begin + 16; ++r) {
+        const int rr = row0 + r;
+        if (rr >= p.rows_per_batch) break;
+        const size_t grow = (size_t)batch * p.out_rows_per_batch + rr;
+        switch (p.ldo) {
+            case 512: ln_row<4>(p, grow, lane); break;
+            case 768: ln_row<6>(p, grow, lane); break;
+            case 1024: ln_row<8>(p, grow, lane); break;
+            default: ln_row<10>(p, grow, lane); break;
+        }
+    }
+}
+
 template <int BLOCK_N, int BLOCK_K>
 __global__ void __launch_bounds__(kThreads, 1) gemm_bf16x3_kernel(const __grid_constant__ GemmParams p) {
     using Cfg = GemmCfg<BLOCK_N, BLOCK_K>;
@@ -632,6 +694,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
                 if (leader) mbar_arrive(&tmem_empty[acc]);
                 else mbar_arrive_remote(&tmem_empty[acc], 0);
             }
+            if (p.ln_gamma != nullptr) {
+                // ---- fused LayerNorm: the last CTA to finish its n-tile of these 128 rows normalises them ------------
+                // (all 8 epilogue warps of this CTA take part; named barrier 1 = the epilogue warps only)
+                uint32_t* last_flag = reinterpret_cast<uint32_t*>(smem + k2Stages * k2StageBytes + 192);
+                asm volatile("bar.sync 1, 256;" ::: "memory");  // every warp's stores of this tile are issued
+                if (warp == 4 && lane == 0) {
+                    __threadfence();  // release: this CTA's part of the rows is visible device-wide
+                    const int rb = batch * p.tiles_m_per_batch + row0 / kBlockM;
+                    const unsigned int old = atomicAdd(p.ln_counter + rb, 1u);
+                    const bool last = old == (unsigned int)(p.n_tiles - 1);
+                    if (last) p.ln_counter[rb] = 0;  // ready for the next launch that uses this counter array
+                    *last_flag = last ? 1u : 0u;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (*last_flag != 0u) {
+                    __threadfence();  // acquire: the other CTAs' stores
+                    ln_tile_rows(&p, batch, row0, warp - 4, lane);
+                }
+            }
             if (etr) p.trace[ntile_done == 0 ? 6 : 8] = (unsigned long long)clock64();
             if (++acc == 2) acc = 0, acc_phase ^= 1u;
         }
@@ -659,6 +740,10 @@ static cudaError_t launch_pair(const GemmParams& p, int sm_count, cudaStream_t s
     }
     // umma_n / 2 columns per epilogue warp group, in 32-column chunks
     if ((p.umma_n != 256 && p.umma_n != 192 && p.umma_n != 128) || p.block_k != k2BlockK) return cudaErrorInvalidValue;
+    if (p.ln_gamma != nullptr &&
+        (p.out_f32 == nullptr || p.ln_counter == nullptr || p.qkv_mode || p.n_tiles * p.umma_n != p.ldo ||
+         (p.ldo != 512 && p.ldo != 768 && p.ldo != 1024 && p.ldo != 1280)))
+        return cudaErrorInvalidValue;
     const int num_pt = p.batches * ((p.tiles_m_per_batch + 1) / 2) * p.n_tiles;
     if (num_pt <= 0) return cudaSuccess;
     const int clusters = num_pt < sm_count / 2 ? num_pt : sm_count / 2;

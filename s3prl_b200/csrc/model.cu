@@ -153,7 +153,7 @@ struct Workspace {
     void* book_host = nullptr;
     size_t book_host_bytes = 0;
     cudaEvent_t book_copied = nullptr;  // the previous call's H2D copy has been consumed: the mirror may be rewritten
-    DevBuf wav_stats, wav_pad, c0_part, c0_ss, conv_f32, tmp_f32, x_f32, x1_f32, gate, pos_z;
+    DevBuf wav_stats, wav_pad, c0_part, c0_ss, conv_f32, tmp_f32, x_f32, x1_f32, gate, pos_z, ln_counters;
     SplitBuf act[kNumConv], ln512_s, x_s, xs_s, q_s, k_s, vt_s, ctx_s, x1_s, h_s;
     cudaStream_t stream = nullptr;  // lane stream (lane 1; lane 0 runs on the caller's stream)
     cudaEvent_t done = nullptr;
@@ -549,16 +549,31 @@ static int use_cta_pairs(int umma_n) { return ((umma_n == 256 || umma_n == 128) 
 // Tile width for a flat [M][N] linear layer on CTA pairs: 256 columns unless the (256 x 256)-tile count leaves most
 // of the 74 clusters idle or badly quantised (small per-GPU batches when the utterances are sharded over 8 GPUs);
 // cost ~ rounds x (columns + fixed per-tile overhead).
-static int pick_pair_umma_n(int64_t M, int N, int sm_count) {
+static int g_force_pair_un = 0;  // s3b_gemm_bench: force the pair-tile width (tile-shape sweeps)
+
+// Tile width for a flat [M][N] linear layer on CTA pairs: 256 or 128 columns, from a cost model fitted to the sweep
+// in profiles/r2c_gemm_tile_sweep.txt (tools/gemm_tile_sweep.py; both widths give bit-identical results). Per tile
+//   t_mma = K x 12 cycles per 128 columns (3 MMAs per 16-wide k-step at M = 256), x 1.15 for 128-wide tiles, which
+//           stage the A operand twice as often per unit of tensor work (shared-memory bound at many rounds);
+//   t_epi = cycles per 128 columns of the epilogue: 8.8 k fp32 output, 11 k bf16 hi/lo output, 13.5 k GELU + hi/lo.
+// A cluster runs `rounds` tiles back to back; the epilogue of tile i overlaps the MMAs of tile i+1:
+//   cost = t_mma + (rounds - 1) x max(t_mma, t_epi) + t_epi.
+// What it changes vs the round-1 rule: at the token counts of the sharded runs (M = 1 000 ... 8 000) the exposed
+// epilogue of the last 256-wide tile costs more than a second round of 128-wide tiles (QKV / fc1: -9 ... -11 %).
+static int pick_pair_umma_n(int64_t M, int N, int K, int epi_kind, int sm_count) {
+    if (g_force_pair_un != 0 && N % g_force_pair_un == 0) return g_force_pair_un;
     if (N % 256 != 0) return (N % 128 == 0) ? 128 : 0;
     const int clusters = sm_count / 2 > 0 ? sm_count / 2 : 1;
     const int64_t pairs = ((M + 127) / 128 + 1) / 2;
+    const double epi128 = epi_kind == 2 ? 13500.0 : (epi_kind == 1 ? 11000.0 : 8800.0);
     int best = 256;
     double best_cost = 1e30;
     for (int un = 256; un >= 128; un -= 128) {
         const int64_t tiles = pairs * (N / un);
         const int64_t rounds = (tiles + clusters - 1) / clusters;
-        const double cost = (double)rounds * (un + 48);
+        const double t_mma = (double)K * 12.0 * (un / 128) * (un == 128 ? 1.15 : 1.0);
+        const double t_epi = epi128 * (un / 128);
+        const double cost = t_mma + (double)(rounds - 1) * (t_mma > t_epi ? t_mma : t_epi) + t_epi;
         if (cost < best_cost - 1e-9) best_cost = cost, best = un;
     }
     return best;
@@ -580,13 +595,16 @@ static int pick_umma_n(int N) {
     } while (0)
 
 // out[M][N] = A[M][K] * W[N][K]^T, flat token-major A (hi/lo planes), K % 64 == 0
+// epi_kind: 0 = fp32 output, 1 = bf16 hi/lo output (QKV scatter included), 2 = GELU + hi/lo (tile-width choice only)
 static int linear_params(GemmParams& p, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo,
-                         const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int64_t M, int N, int K) {
+                         const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int64_t M, int N, int K,
+                         int epi_kind = 0) {
     memset(&p, 0, sizeof(p));
     if (K % 64 != 0 || N % 16 != 0)  // K % 64 keeps both k-block widths legal
         return fail("linear: K %% 64 or N %% 16 violated (N=%d K=%d)", N, K);
     int un = pick_umma_n(N);
-    if (pairs_enabled() && pick_pair_umma_n(M, N, g_sm_count) != 0) un = pick_pair_umma_n(M, N, g_sm_count);
+    if (pairs_enabled() && pick_pair_umma_n(M, N, K, epi_kind, g_sm_count) != 0)
+        un = pick_pair_umma_n(M, N, K, epi_kind, g_sm_count);
     const int pair = use_cta_pairs(un);
     const int bk = pair ? 64 : gemm_block_k(un);
     const int bbox = pair ? un / 2 : un;  // CTA pairs: each CTA loads half of the tile's W rows
@@ -702,6 +720,17 @@ static inline void prof_end(s3b_model* m, cudaStream_t st, int cat, int nkernels
 #define KCONV0(nk, expr) KLAUNCH(CAT_CONV0, nk, conv0_flops, expr)
 #define KMISC(expr) KLAUNCH(CAT_MISC, 1, 0.0, expr)
 
+// LayerNorm fused into the producing GEMM (gemm.cuh: ln_*): on unless S3B_FUSE_LN=0 (kept for A/B measurements)
+static bool fuse_ln_enabled() {
+    const char* e = getenv("S3B_FUSE_LN");  // read per call: tests toggle it (the plan cache is keyed on it)
+    return !(e != nullptr && e[0] == '0') && pairs_enabled();
+}
+static void set_ln(GemmParams& p, const float* gamma, const float* beta, int gelu, float* out_f32, __nv_bfloat16* hi,
+                   __nv_bfloat16* lo, unsigned int* counter) {
+    p.ln_gamma = gamma, p.ln_beta = beta, p.ln_gelu = gelu, p.ln_out_f32 = out_f32, p.ln_out_hi = hi, p.ln_out_lo = lo;
+    p.ln_counter = counter;
+}
+
 // ------------------------------------------------------------------------------------------------
 // cached launch plan: every tensor map / GEMM descriptor of one forward at a given (B, Lmax)
 // ------------------------------------------------------------------------------------------------
@@ -717,13 +746,15 @@ struct Plan {
     int B = 0;
     int64_t Lmax = 0;
     uint64_t gen = 0;
+    bool fuse_ln = false;
     GemmParams conv[kNumConv];
     GemmParams proj, pos;
     std::vector<LayerPlan> layers;
 };
 
 void Workspace::release() {
-    DevBuf* bufs[] = {&book, &wav_stats, &wav_pad, &c0_part, &c0_ss, &conv_f32, &tmp_f32, &x_f32, &x1_f32, &gate, &pos_z};
+    DevBuf* bufs[] = {&book, &wav_stats, &wav_pad, &c0_part, &c0_ss, &conv_f32, &tmp_f32, &x_f32, &x1_f32, &gate, &pos_z,
+                      &ln_counters};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < kNumConv; ++i) act[i].release();
     SplitBuf* sb[] = {&ln512_s, &x_s, &xs_s, &q_s, &k_s, &vt_s, &ctx_s, &x1_s, &h_s};
@@ -769,6 +800,8 @@ struct Fwd {
     long long* d_lens = nullptr;
     int* d_kv = nullptr;
     uint8_t* d_mask = nullptr;
+    bool fuse_ln = false;
+    unsigned int* cnt[2] = {nullptr, nullptr};  // two alternating row-block counter arrays of the fused LayerNorm
 
     int num_stages() const { return 9 + 5 * m->cfg.num_layers; }
     int prepare();
@@ -850,12 +883,19 @@ int Fwd::prepare() {
     S3B_OK(w->h_s.ensure((size_t)M * F));
     if (posconv4_ok(c)) S3B_OK(w->pos_z.ensure((size_t)B * (T + 3) * 4 * D * sizeof(float)));
     if (c.relative_position) S3B_OK(w->gate.ensure((size_t)B * H * T * 4));
+    fuse_ln = fuse_ln_enabled();
+    {
+        const size_t n_cnt = (size_t)B * (L[1] / 128 + 2) + (size_t)M / 128 + 16;
+        S3B_OK(w->ln_counters.ensure(2 * n_cnt * sizeof(unsigned int)));
+        cnt[0] = w->ln_counters.as<unsigned int>();
+        cnt[1] = cnt[0] + n_cnt;
+    }
 
     // ---- launch plan (cached per (B, Lmax) while no buffer has been reallocated) --------------------------------
     plan = nullptr;
     for (size_t i = 0; i < w->plans.size(); ++i) {
         Plan* pl = w->plans[i];
-        if (pl->B == B && pl->Lmax == Lmax && pl->gen == g_alloc_generation) {
+        if (pl->B == B && pl->Lmax == Lmax && pl->gen == g_alloc_generation && pl->fuse_ln == fuse_ln) {
             plan = pl;
             w->plans.erase(w->plans.begin() + i);
             w->plans.insert(w->plans.begin(), pl);
@@ -869,7 +909,7 @@ int Fwd::prepare() {
             delete pl;
             return r;
         }
-        pl->B = B, pl->Lmax = Lmax, pl->gen = g_alloc_generation;
+        pl->B = B, pl->Lmax = Lmax, pl->gen = g_alloc_generation, pl->fuse_ln = fuse_ln;
         w->plans.insert(w->plans.begin(), pl);
         while (w->plans.size() > 4) {
             delete w->plans.back();
@@ -898,10 +938,13 @@ int Fwd::build_plan(Plan& pl) {
             else e.out_hi = w->act[i].h(), e.out_lo = w->act[i].l();
         }
         set_epi(p, e, C);
+        if (c.extractor_layer_norm && fuse_ln && p.two_cta)  // per-frame LayerNorm(512) + GELU (wav2vec2_model.py:2887-2897)
+            set_ln(p, m->conv_ln_g[i].as<float>(), m->conv_ln_b[i].as<float>(), 1, last ? w->conv_f32.as<float>() : nullptr,
+                   last ? nullptr : w->act[i].h(), last ? nullptr : w->act[i].l(), cnt[i & 1]);
     }
     {
         GemmParams& p = pl.proj;
-        S3B_OK(linear_params(p, w->ln512_s.h(), w->ln512_s.l(), m->proj_w.h(), m->proj_w.l(), M, D, C));
+        S3B_OK(linear_params(p, w->ln512_s.h(), w->ln512_s.l(), m->proj_w.h(), m->proj_w.l(), M, D, C, 1));
         Epi e;
         e.bias = m->proj_b.as<float>();
         e.row_mask = d_mask;  // x[padding_mask] = 0 (wav2vec2_model.py:3061-3062)
@@ -933,7 +976,7 @@ int Fwd::build_plan(Plan& pl) {
         LayerPlan& lp = pl.layers[l];
         {   // QKV projection, scattered per head; q pre-scaled by head_dim^-0.5 (exact power of two) and log2(e)
             GemmParams& p = lp.qkv;
-            S3B_OK(linear_params(p, w->xs_s.h(), w->xs_s.l(), W.qkv.h(), W.qkv.l(), M, 3 * D, D));
+            S3B_OK(linear_params(p, w->xs_s.h(), w->xs_s.l(), W.qkv.h(), W.qkv.l(), M, 3 * D, D, 1));
             Epi e;
             e.bias = W.qkv_b.as<float>();
             set_epi(p, e, 3 * D);
@@ -966,10 +1009,17 @@ int Fwd::build_plan(Plan& pl) {
             e.bias = W.out_b.as<float>();
             e.out_f32 = c.layer_norm_first ? w->x1_f32.as<float>() : w->tmp_f32.as<float>();
             set_epi(p, e, D);
+            if (fuse_ln && p.two_cta) {
+                if (c.layer_norm_first)  // x1_s = LN2(r1), r1 = x1_f32
+                    set_ln(p, W.ln2_g.as<float>(), W.ln2_b.as<float>(), 0, nullptr, w->x1_s.h(), w->x1_s.l(), cnt[0]);
+                else  // x1 = LN1(x + attn)
+                    set_ln(p, W.ln1_g.as<float>(), W.ln1_b.as<float>(), 0, w->x1_f32.as<float>(), w->x1_s.h(), w->x1_s.l(),
+                           cnt[0]);
+            }
         }
         {   // fc1 + GELU
             GemmParams& p = lp.fc1;
-            S3B_OK(linear_params(p, w->x1_s.h(), w->x1_s.l(), W.fc1.h(), W.fc1.l(), M, F, D));
+            S3B_OK(linear_params(p, w->x1_s.h(), w->x1_s.l(), W.fc1.h(), W.fc1.l(), M, F, D, 2));
             Epi e;
             e.bias = W.fc1_b.as<float>();
             e.gelu = 1;
@@ -984,6 +1034,17 @@ int Fwd::build_plan(Plan& pl) {
             e.residual = w->x1_f32.as<float>();
             e.out_f32 = w->tmp_f32.as<float>();
             set_epi(p, e, D);
+            if (fuse_ln && p.two_cta) {
+                const bool last = (l == NL - 1);
+                if (!c.layer_norm_first)  // hidden state l+1 = LN2(x1 + ffn) (fp32 output patched per call) + operand of layer l+1
+                    set_ln(p, W.ln2_g.as<float>(), W.ln2_b.as<float>(), 0, nullptr, last ? nullptr : w->xs_s.h(),
+                           last ? nullptr : w->xs_s.l(), cnt[1]);
+                else if (last)  // encoder.layer_norm on the final output (wav2vec2_model.py:3049-3050), output patched per call
+                    set_ln(p, m->enc_ln_g.as<float>(), m->enc_ln_b.as<float>(), 0, nullptr, nullptr, nullptr, cnt[1]);
+                else  // pre-LN: the NEXT layer's LN1 of the residual stream this GEMM produces
+                    set_ln(p, m->layers[l + 1].ln1_g.as<float>(), m->layers[l + 1].ln1_b.as<float>(), 0, nullptr,
+                           w->xs_s.h(), w->xs_s.l(), cnt[1]);
+            }
         }
     }
     return 0;
@@ -1022,7 +1083,7 @@ int Fwd::stage(int s) {
         const int i = s;
         GemmParams p = plan->conv[i];
         KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
-        if (c.extractor_layer_norm) {
+        if (c.extractor_layer_norm && p.ln_gamma == nullptr) {
             const bool last = (i == kNumConv - 1);
             KNORM(launch_layernorm(w->conv_f32.as<float>(), (size_t)B * L[i], C, m->conv_ln_g[i].as<float>(),
                                    m->conv_ln_b[i].as<float>(), 1, last ? w->conv_f32.as<float>() : nullptr,
@@ -1070,7 +1131,8 @@ int Fwd::stage(int s) {
     const bool rel = c.relative_position != 0;
     switch (sub) {
         case 0: {
-            if (c.layer_norm_first)  // xs = LN1(residual stream)
+            // pre-LN: xs = LN1(residual stream); from layer 1 on it is produced by the previous layer's fc2 epilogue
+            if (c.layer_norm_first && (l == 0 || plan->layers[l - 1].fc2.ln_gamma == nullptr))
                 KNORM(launch_layernorm(hs_in, (size_t)M, D, W.ln1_g.as<float>(), W.ln1_b.as<float>(), 0, nullptr,
                                        w->xs_s.h(), w->xs_s.l(), st));
             GemmParams p = lp.qkv;
@@ -1089,6 +1151,7 @@ int Fwd::stage(int s) {
             GemmParams p = lp.out;
             p.residual = hs_in;
             KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
+            if (p.ln_gamma != nullptr) return 0;  // LayerNorm fused into the GEMM
             if (c.layer_norm_first)  // x1_s = LN2(r1), r1 = x1_f32
                 KNORM(launch_layernorm(w->x1_f32.as<float>(), (size_t)M, D, W.ln2_g.as<float>(), W.ln2_b.as<float>(), 0,
                                        nullptr, w->x1_s.h(), w->x1_s.l(), st));
@@ -1108,7 +1171,12 @@ int Fwd::stage(int s) {
             float* unnorm = (last && last_res != nullptr) ? last_res : w->tmp_f32.as<float>();
             if (c.layer_norm_first) p.out_f32 = last ? unnorm : hs_out;
             if (ffn_out != nullptr) p.out_pre = ffn_out + (size_t)l * ffn_stride;
+            if (p.ln_gamma != nullptr && (!c.layer_norm_first || last)) p.ln_out_f32 = hs_out;
             KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
+            if (p.ln_gamma != nullptr) {
+                if (layer_done) S3B_OK(layer_done(m, l + 1, st, user));
+                return 0;
+            }
             if (c.layer_norm_first) {
                 if (last)  // encoder.layer_norm on the final output (wav2vec2_model.py:3049-3050)
                     KNORM(launch_layernorm(unnorm, (size_t)M, D, m->enc_ln_g.as<float>(), m->enc_ln_b.as<float>(), 0,
@@ -1503,6 +1571,53 @@ extern "C" int s3b_linear_f32(const float* a, const float* w, const float* bias,
     cudaError_t se = cudaStreamSynchronize(st);
     as.release(), ws.release();
     if (r == 0 && se != cudaSuccess) return fail("gemm execution failed: %s", cudaGetErrorString(se));
+    return r;
+}
+
+// Times `iters` back-to-back launches of the production GEMM (bias + GELU + split epilogue like fc1 when gelu != 0,
+// bias + residual + fp32 output like out_proj / fc2 otherwise) on random operands; force_un in {0, 128, 256}.
+extern "C" int s3b_gemm_bench(int64_t M, int32_t N, int32_t K, int32_t gelu, int32_t force_un, int32_t iters,
+                              float* ms_per_launch) {
+    if (!ms_per_launch || iters < 1) return fail("bad argument");
+    int sms = 0;
+    S3B_OK(device_sm_count(&sms));
+    g_sm_count = sms;
+    SplitBuf as, ws, os;
+    DevBuf bias, res, out;
+    S3B_OK(as.ensure((size_t)M * K));
+    S3B_OK(ws.ensure((size_t)N * K));
+    S3B_OK(bias.ensure((size_t)N * 4));
+    S3B_OK(res.ensure((size_t)M * N * 4));
+    S3B_OK(out.ensure((size_t)M * N * 4));
+    S3B_OK(os.ensure((size_t)M * N));
+    // finite, non-trivial operand bits: bf16 0x3c00..0x3cff ~ 0.0078..0.031
+    CUDA_OK(cudaMemset(as.hi.p, 0x3c, (size_t)M * K * 2));
+    CUDA_OK(cudaMemset(ws.hi.p, 0x3c, (size_t)N * K * 2));
+    GemmParams p;
+    g_force_pair_un = force_un;
+    int r = linear_params(p, as.h(), as.l(), ws.h(), ws.l(), M, N, K, gelu ? 2 : 0);
+    g_force_pair_un = 0;
+    if (r == 0) {
+        Epi e;
+        e.bias = bias.as<float>();
+        if (gelu) e.gelu = 1, e.out_hi = os.h(), e.out_lo = os.l();
+        else e.residual = res.as<float>(), e.out_f32 = out.as<float>();
+        set_epi(p, e, N);
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0), cudaEventCreate(&e1);
+        for (int i = 0; i < 3; ++i) launch_gemm_bf16x3(p, sms, 0);
+        cudaEventRecord(e0, 0);
+        for (int i = 0; i < iters; ++i) launch_gemm_bf16x3(p, sms, 0);
+        cudaEventRecord(e1, 0);
+        cudaError_t ce = cudaDeviceSynchronize();
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *ms_per_launch = ms / iters;
+        cudaEventDestroy(e0), cudaEventDestroy(e1);
+        if (ce != cudaSuccess) r = fail("gemm bench failed: %s", cudaGetErrorString(ce));
+        else if (ms_per_launch[0] >= 0) ms_per_launch[1] = (float)p.umma_n;
+    }
+    as.release(), ws.release(), os.release(), bias.release(), res.release(), out.release();
     return r;
 }
 

@@ -43,6 +43,7 @@ EXPORTED_SYMBOLS = [
     "s3b_weighted_sum_backward",
     "s3b_linear_f32",
     "s3b_layernorm_f32",
+    "s3b_gemm_bench",
     "s3b_attention_f32",
     "s3b_fbank",
     "s3b_fbank_num_frames",
@@ -148,6 +149,7 @@ def load() -> C.CDLL:
     lib.s3b_weighted_sum.argtypes = [f32p, i32, i64, f32p, f32p, vp]
     lib.s3b_weighted_sum_backward.argtypes = [f32p, i32, i64, f32p, f32p, vp]
     lib.s3b_linear_f32.argtypes = [f32p, f32p, f32p, f32p, i64, i32, i32, i32, f32p, vp]
+    lib.s3b_gemm_bench.argtypes = [i64, i32, i32, i32, i32, i32, C.POINTER(C.c_float)]
     lib.s3b_layernorm_f32.argtypes = [f32p, i64, i32, f32p, f32p, i32, f32p, vp]
     lib.s3b_attention_f32.argtypes = [f32p, f32p, f32p, C.POINTER(i32), i32, i32, i32, f32p, vp]
     lib.s3b_fbank_num_frames.argtypes = [i64]

@@ -237,3 +237,23 @@ def test_local_checkpoint_entries(s3b_lib, tmp_path):
         a = torch.stack(hub.ENTRIES[name]().to("cuda")(wavs)["hidden_states"])
         b = torch.stack(hub.ENTRIES[local](str(path)).to("cuda")(wavs)["hidden_states"])
         assert torch.equal(a, b), name
+
+
+@pytest.mark.parametrize("name", ["hubert_base", "wav2vec2_large_ll60k", "wavlm_base_plus", "wavlm_large"])
+def test_fused_layernorm_is_bit_identical(s3b_lib, name):
+    """LayerNorm fused into the producing GEMM (last CTA to finish a 128-row block normalises it) == the separate
+    layernorm_kernel launches, bit for bit: post-LN and pre-LN encoders, per-frame conv LayerNorm + GELU."""
+    expert = _expert(name)
+    wavs = [w.cuda() for w in _wavs([20000, 16001, 5000], seed=31)]
+    os.environ["S3B_FUSE_LN"] = "0"
+    try:
+        ref = torch.stack(expert(wavs)["hidden_states"]).clone()
+    finally:
+        os.environ.pop("S3B_FUSE_LN", None)
+    for lanes in (1, 2):
+        expert.lanes = lanes
+        try:
+            got = torch.stack(expert(wavs)["hidden_states"])
+        finally:
+            expert.lanes = 0
+        assert torch.equal(got, ref), (name, lanes)
