@@ -332,17 +332,11 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
             tmem_ld_32x32(tmem_o + lane_off + (uint32_t)(half * kDCols + c), v);
             tmem_ld_wait();
             if (row_ok) {
-                uint4* dh = reinterpret_cast<uint4*>(p.ctx_hi + off + c);
-                uint4* dl = reinterpret_cast<uint4*>(p.ctx_lo + off + c);
 #pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    uint32_t hw[4], lw[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        split_pack2(__uint_as_float(v[i + 2 * e]) * inv, __uint_as_float(v[i + 2 * e + 1]) * inv, hw[e],
-                                    lw[e]);
-                    dh[i >> 3] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                    dl[i >> 3] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 y = make_float4(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv,
+                                                 __uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
+                    store_planes4(p.ctx, y, off + c + i);
                 }
             }
         }

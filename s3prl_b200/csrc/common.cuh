@@ -80,6 +80,107 @@ __device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
 }
 
+// ----------------------------------------------------------------------------------------------
+// "f16q8" operand format: x ~= h16 + l8 * 2^-kQ8ShiftA with h16 = fp16_rn(x) and two e4m3 planes
+//   h8 = e4m3(h16)                        (the operand of the  A_hi * W_lo  correction MMA)
+//   l8 = e4m3((x - h16) * 2^kQ8ShiftA)    (the operand of the  A_lo * W_hi  correction MMA)
+// Weights: w16 = fp16_rn(w), wh8 = e4m3(w * 2^kQ8ShiftB), wl8 = e4m3((w - w16) * 2^kQ8ShiftD). Both correction
+// products therefore carry the factor 2^kQ8Scale (= ShiftA + ShiftB = ShiftD); they are accumulated FIRST and the first
+// main fp16 MMA of a tile scales the accumulator back with tcgen05.mma's scale-input-d immediate (D = A*B + D * 2^-15).
+// 4 bytes per activation element, like the bf16 hi/lo pair it replaces; 8 instructions per element pair.
+// ----------------------------------------------------------------------------------------------
+static constexpr int kQ8ShiftA = 11;  // activations: residual of an 11-bit significand, scaled into e4m3's range
+static constexpr int kQ8ShiftB = 4;   // weights |w| <= 28 stay finite in e4m3 (satfinite clamps beyond)
+static constexpr int kQ8ShiftD = 15;  // weight residuals (|w - w16| <= 2^-11 |w|)
+static constexpr int kQ8Scale = 15;   // = kQ8ShiftA + kQ8ShiftB = kQ8ShiftD (activation h8 plane is unscaled)
+static_assert(kQ8ShiftA + kQ8ShiftB == kQ8Scale && kQ8ShiftD == kQ8Scale, "correction products must share one scale");
+
+// two floats -> fp16x2 word (element 0 in the low half), e4m3x2 of the fp16 values, e4m3x2 of the scaled residuals
+__device__ __forceinline__ void split_q8_pack2(float a, float b, uint32_t& h16, uint16_t& h8, uint16_t& l8) {
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h16) : "f"(b), "f"(a));
+    asm("cvt.rn.satfinite.e4m3x2.f16x2 %0, %1;" : "=h"(h8) : "r"(h16));
+    float ha, hb;
+    asm("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %2; cvt.f32.f16 %0, lo; cvt.f32.f16 %1, hi; }"
+        : "=f"(ha), "=f"(hb)
+        : "r"(h16));
+    float ra, rb;
+    fsub2(ra, rb, a, b, ha, hb);
+    const float sc = (float)(1 << kQ8ShiftA);
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(l8) : "f"(rb * sc), "f"(ra * sc));
+}
+// four consecutive elements -> one 8-byte fp16 store + two 4-byte e4m3 stores
+__device__ __forceinline__ void store_q8x4(const float4& y, __nv_bfloat16* p16, uint8_t* ph8, uint8_t* pl8, size_t elem) {
+    uint32_t h0, h1;
+    uint16_t a0, a1, b0, b1;
+    split_q8_pack2(y.x, y.y, h0, a0, b0);
+    split_q8_pack2(y.z, y.w, h1, a1, b1);
+    *reinterpret_cast<uint2*>(p16 + elem) = make_uint2(h0, h1);
+    *reinterpret_cast<uint32_t*>(ph8 + elem) = (uint32_t)a0 | ((uint32_t)a1 << 16);
+    *reinterpret_cast<uint32_t*>(pl8 + elem) = (uint32_t)b0 | ((uint32_t)b1 << 16);
+}
+
+// GEMM-operand output of a producer kernel (LayerNorm, conv-0, GEMM epilogues, attention, pos_conv combine):
+// fmt 0 = bf16 hi / lo planes (bf16x3 scheme), fmt 1 = fp16 plane + two e4m3 planes (f16q8 scheme).
+struct OutPlanes {
+    __nv_bfloat16* hi;
+    __nv_bfloat16* lo;
+    uint8_t* h8;
+    uint8_t* l8;
+    int fmt;
+};
+__host__ __device__ inline OutPlanes no_planes() { return OutPlanes{nullptr, nullptr, nullptr, nullptr, 0}; }
+
+// four consecutive elements starting at element index `elem` (elem % 4 == 0)
+__device__ __forceinline__ void store_planes4(const OutPlanes& o, const float4& y, size_t elem) {
+    if (o.fmt != 0) {
+        store_q8x4(y, o.hi, o.h8, o.l8, elem);
+    } else {
+        uint32_t h0, l0, h1, l1;
+        split_pack2(y.x, y.y, h0, l0);
+        split_pack2(y.z, y.w, h1, l1);
+        *reinterpret_cast<uint2*>(o.hi + elem) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(o.lo + elem) = make_uint2(l0, l1);
+    }
+}
+// two consecutive elements (elem % 2 == 0)
+__device__ __forceinline__ void store_planes2(const OutPlanes& o, float y0, float y1, size_t elem) {
+    if (o.fmt != 0) {
+        uint32_t h;
+        uint16_t a, b;
+        split_q8_pack2(y0, y1, h, a, b);
+        *reinterpret_cast<uint32_t*>(o.hi + elem) = h;
+        *reinterpret_cast<uint16_t*>(o.h8 + elem) = a;
+        *reinterpret_cast<uint16_t*>(o.l8 + elem) = b;
+    } else {
+        uint32_t h, l;
+        split_pack2(y0, y1, h, l);
+        *reinterpret_cast<uint32_t*>(o.hi + elem) = h;
+        *reinterpret_cast<uint32_t*>(o.lo + elem) = l;
+    }
+}
+// read back element pair `elem` (even) of an operand in either format
+__device__ __forceinline__ float2 load_planes2(const OutPlanes& o, size_t elem) {
+    const uint32_t h = *reinterpret_cast<const uint32_t*>(o.hi + elem);
+    if (o.fmt != 0) {
+        const uint16_t l = *reinterpret_cast<const uint16_t*>(o.l8 + elem);
+        float h0, h1;
+        asm("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %2; cvt.f32.f16 %0, lo; cvt.f32.f16 %1, hi; }"
+            : "=f"(h0), "=f"(h1)
+            : "r"(h));
+        uint32_t lf;  // e4m3x2 -> f16x2
+        asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(lf) : "h"(l));
+        float l0, l1;
+        asm("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %2; cvt.f32.f16 %0, lo; cvt.f32.f16 %1, hi; }"
+            : "=f"(l0), "=f"(l1)
+            : "r"(lf));
+        const float inv = 1.0f / (float)(1 << kQ8ShiftA);
+        return make_float2(fmaf(l0, inv, h0), fmaf(l1, inv, h1));
+    }
+    const uint32_t l = *reinterpret_cast<const uint32_t*>(o.lo + elem);
+    return make_float2(__uint_as_float(h << 16) + __uint_as_float(l << 16),
+                       __uint_as_float(h & 0xffff0000u) + __uint_as_float(l & 0xffff0000u));
+}
+
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -314,6 +415,31 @@ __device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a,
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// kind::f8f6f4 (e4m3 x e4m3, K = 32 per instruction, fp32 accumulate), CTA pair
+__device__ __forceinline__ void umma_q8_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// kind::f16 with the scale-input-d immediate: D = A*B + D * 2^-kQ8Scale
+__device__ __forceinline__ void umma_f16_2cta_scaled(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                                     uint32_t idesc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, 1, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p, 15;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc)
+        : "memory");
+}
+static_assert(kQ8Scale == 15, "the scale-input-d immediate above is spelled out as 15");
 // commit of the pair's MMAs, arriving on the same barrier offset in BOTH CTAs (mask 0b11)
 __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
     asm volatile(
@@ -357,6 +483,10 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
     d |= (uint64_t)2 << 61;                         // layout type: SWIZZLE_128B
     return d;
+}
+// Instruction descriptor with A = B = fp16 (kind::f16) — the same bits select e4m3 x e4m3 under kind::f8f6f4.
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N) {
+    return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 // Instruction descriptor: kind::f16, A=B=bf16 (K-major), D=fp32, M x N tile.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {

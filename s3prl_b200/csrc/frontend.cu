@@ -33,6 +33,45 @@ cudaError_t launch_split(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, s
     return cudaGetLastError();
 }
 
+// fp32 -> f16q8 planes (common.cuh): activations (weight == 0) or weights (weight != 0: wh8 = e4m3(w * 2^ShiftB),
+// wl8 = e4m3((w - w16) * 2^ShiftD))
+__global__ void split_q8_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ p16,
+                                uint8_t* __restrict__ h8, uint8_t* __restrict__ l8, size_t n2, int weight) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n2; i += stride) {
+        const float a = x[2 * i], b = x[2 * i + 1];
+        uint32_t h;
+        uint16_t q_h, q_l;
+        if (weight == 0) {
+            split_q8_pack2(a, b, h, q_h, q_l);
+        } else {
+            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));
+            float ha, hb;
+            asm("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %2; cvt.f32.f16 %0, lo; cvt.f32.f16 %1, hi; }"
+                : "=f"(ha), "=f"(hb)
+                : "r"(h));
+            const float sb = (float)(1 << kQ8ShiftB), sd = (float)(1 << kQ8ShiftD);
+            asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(q_h) : "f"(b * sb), "f"(a * sb));
+            asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(q_l) : "f"((b - hb) * sd), "f"((a - ha) * sd));
+        }
+        reinterpret_cast<uint32_t*>(p16)[i] = h;
+        reinterpret_cast<uint16_t*>(h8)[i] = q_h;
+        reinterpret_cast<uint16_t*>(l8)[i] = q_l;
+    }
+}
+
+cudaError_t launch_split_q8(const float* x, __nv_bfloat16* p16, uint8_t* h8, uint8_t* l8, size_t n, int weight,
+                            cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    if (n & 1) return cudaErrorInvalidValue;
+    const size_t n2 = n / 2;
+    size_t blocks = (n2 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    split_q8_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, p16, h8, l8, n2, weight);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 // pack B ragged waveforms into a zero-padded [B][Lpad] buffer; optional F.layer_norm(wav, wav.shape)
 // (eps 1e-5, biased variance) per utterance (task_cfg.normalize, hubert/expert.py:57-58)
@@ -217,9 +256,7 @@ __global__ void __launch_bounds__(kC0) conv0_finalize_kernel(const float* __rest
 __global__ void __launch_bounds__(256) conv0_apply_gn_kernel(const float* __restrict__ x, long long L, int L0,
                                                              const float* __restrict__ w,
                                                              const float* __restrict__ scale,
-                                                             const float* __restrict__ shift,
-                                                             uint32_t* __restrict__ out_hi,
-                                                             uint32_t* __restrict__ out_lo) {
+                                                             const float* __restrict__ shift, const OutPlanes op) {
     __shared__ __align__(16) float xs[kXTile];
     const int b = blockIdx.y;
     const int t0 = blockIdx.x * kTCH;
@@ -232,8 +269,7 @@ __global__ void __launch_bounds__(256) conv0_apply_gn_kernel(const float* __rest
     const float sh0 = shift[b * kC0 + c0], sh1 = shift[b * kC0 + c0 + 1];
     __syncthreads();
     const int nt = min(kTCH, L0 - t0);
-    uint32_t* oh = out_hi + ((size_t)b * L0 + t0) * (kC0 / 2) + threadIdx.x;
-    uint32_t* ol = out_lo + ((size_t)b * L0 + t0) * (kC0 / 2) + threadIdx.x;
+    const size_t e0 = ((size_t)b * L0 + t0) * kC0 + c0;  // element index of (frame t0, channel c0)
     for (int tl = 0; tl < nt; tl += 4) {
         float z0[4], z1[4];
         conv0_quad(xs, tl, w0, w1, z0, z1);
@@ -242,10 +278,7 @@ __global__ void __launch_bounds__(256) conv0_apply_gn_kernel(const float* __rest
             if (tl + q < nt) {
                 const float y0 = gelu_erf(fmaf(z0[q], sc0, sh0));
                 const float y1 = gelu_erf(fmaf(z1[q], sc1, sh1));
-                uint32_t h, l;
-                split_pack2(y0, y1, h, l);
-                oh[(size_t)(tl + q) * (kC0 / 2)] = h;
-                ol[(size_t)(tl + q) * (kC0 / 2)] = l;
+                store_planes2(op, y0, y1, e0 + (size_t)(tl + q) * kC0);
             }
         }
     }
@@ -257,9 +290,7 @@ __global__ void __launch_bounds__(256) conv0_apply_ln_kernel(const float* __rest
                                                              const float* __restrict__ w,
                                                              const float* __restrict__ cbias,
                                                              const float* __restrict__ gamma,
-                                                             const float* __restrict__ beta,
-                                                             uint32_t* __restrict__ out_hi,
-                                                             uint32_t* __restrict__ out_lo) {
+                                                             const float* __restrict__ beta, const OutPlanes op) {
     __shared__ __align__(16) float xs[kXTile];
     __shared__ float red[8][4];
     __shared__ float stat[4];
@@ -275,8 +306,7 @@ __global__ void __launch_bounds__(256) conv0_apply_ln_kernel(const float* __rest
     __syncthreads();
     const int nt = min(kTCH, L0 - t0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* oh = out_hi + ((size_t)b * L0 + t0) * (kC0 / 2) + threadIdx.x;
-    uint32_t* ol = out_lo + ((size_t)b * L0 + t0) * (kC0 / 2) + threadIdx.x;
+    const size_t e0 = ((size_t)b * L0 + t0) * kC0 + c0;
     for (int tl = 0; tl < nt; tl += 4) {
         float z0[4], z1[4], mean[4], rstd[4];
         conv0_quad(xs, tl, w0, w1, z0, z1);
@@ -319,10 +349,7 @@ __global__ void __launch_bounds__(256) conv0_apply_ln_kernel(const float* __rest
             if (tl + q < nt) {
                 const float y0 = gelu_erf(fmaf((z0[q] - mean[q]) * rstd[q], g0, be0));
                 const float y1 = gelu_erf(fmaf((z1[q] - mean[q]) * rstd[q], g1, be1));
-                uint32_t h, l;
-                split_pack2(y0, y1, h, l);
-                oh[(size_t)(tl + q) * (kC0 / 2)] = h;
-                ol[(size_t)(tl + q) * (kC0 / 2)] = l;
+                store_planes2(op, y0, y1, e0 + (size_t)(tl + q) * kC0);
             }
         }
     }
@@ -330,26 +357,22 @@ __global__ void __launch_bounds__(256) conv0_apply_ln_kernel(const float* __rest
 
 cudaError_t launch_conv0_groupnorm(const float* x, int B, long long L, int L0, const float* w, const float* gamma,
                                    const float* beta, float* ws_part /*[B][nchunk][65]*/,
-                                   float* ws_scale_shift /*[2][B][512]*/, __nv_bfloat16* out_hi,
-                                   __nv_bfloat16* out_lo, cudaStream_t s) {
+                                   float* ws_scale_shift /*[2][B][512]*/, const OutPlanes& op, cudaStream_t s) {
     const int nchunk = (L0 + kTCH - 1) / kTCH;
     float* scale = ws_scale_shift;
     float* shift = ws_scale_shift + (size_t)B * kC0;
     dim3 grid(nchunk, B);
     conv0_moments_kernel<<<grid, 256, 0, s>>>(x, L, L0, ws_part, nchunk);
     conv0_finalize_kernel<<<B, kC0, 0, s>>>(ws_part, nchunk, L0, w, gamma, beta, scale, shift);
-    conv0_apply_gn_kernel<<<grid, 256, 0, s>>>(x, L, L0, w, scale, shift, reinterpret_cast<uint32_t*>(out_hi),
-                                                reinterpret_cast<uint32_t*>(out_lo));
+    conv0_apply_gn_kernel<<<grid, 256, 0, s>>>(x, L, L0, w, scale, shift, op);
     return cudaGetLastError();
 }
 
 cudaError_t launch_conv0_layernorm(const float* x, int B, long long L, int L0, const float* w, const float* cbias,
-                                   const float* gamma, const float* beta, __nv_bfloat16* out_hi,
-                                   __nv_bfloat16* out_lo, cudaStream_t s) {
+                                   const float* gamma, const float* beta, const OutPlanes& op, cudaStream_t s) {
     const int nchunk = (L0 + kTCH - 1) / kTCH;
     dim3 grid(nchunk, B);
-    conv0_apply_ln_kernel<<<grid, 256, 0, s>>>(x, L, L0, w, cbias, gamma, beta, reinterpret_cast<uint32_t*>(out_hi),
-                                                reinterpret_cast<uint32_t*>(out_lo));
+    conv0_apply_ln_kernel<<<grid, 256, 0, s>>>(x, L, L0, w, cbias, gamma, beta, op);
     return cudaGetLastError();
 }
 

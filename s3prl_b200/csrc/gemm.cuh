@@ -16,6 +16,12 @@ struct GemmParams {
     // B operand (weights, [N][K] K-major): bf16 hi / lo, 3-D tensor maps (k, n, z), box {64, umma_n, 1}
     CUtensorMap b_hi, b_lo;
 
+    // scheme 1 ("f16q8", CTA-pair kernel only): fp16 main product + two e4m3 correction products.
+    //   a_hi / b_hi are the fp16 planes (box {64, rows}), a_h8 / a_l8 / b_h8 / b_l8 the e4m3 planes (box {128, rows});
+    //   k-blocks are 128 elements wide: block_k == 128, K % 128 == 0; a_lo / b_lo are unused.
+    int scheme;
+    CUtensorMap a_h8, a_l8, b_h8, b_l8;
+
     // ---- tiling -------------------------------------------------------------------------------
     int batches;            // extent of A's 3rd dim that is tiled over
     int rows_per_batch;     // valid output rows per batch
@@ -47,6 +53,11 @@ struct GemmParams {
     float* out_f32;
     __nv_bfloat16* out_hi;
     __nv_bfloat16* out_lo;
+    // out_fmt 1: out_hi is an fp16 plane and out_h8 / out_l8 the two e4m3 planes of the f16q8 operand format (same for
+    // the fused LayerNorm outputs); out_fmt 0: out_hi / out_lo are the bf16 hi / lo planes.
+    int out_fmt;
+    uint8_t* out_h8;
+    uint8_t* out_l8;
     float* out_pre;  // optional: v BEFORE the residual add (fc2 output, "fairseq_layers_before_residual"), same layout
 
     // ---- epilogue, QKV scatter mode (qkv_mode != 0): columns [0,D) -> q*scale, [D,2D) -> k, [2D,3D) -> v
@@ -68,6 +79,8 @@ struct GemmParams {
     float* ln_out_f32;
     __nv_bfloat16* ln_out_hi;
     __nv_bfloat16* ln_out_lo;
+    uint8_t* ln_out_h8;
+    uint8_t* ln_out_l8;
     unsigned int* ln_counter;  // [batches * tiles_m_per_batch], zero on entry, left zero
 
     double alg_flops;  // host-side accounting only: 2*M*N*K with the un-padded K
@@ -90,5 +103,8 @@ cudaError_t launch_gemm_bf16x3(const GemmParams& p, int sm_count, cudaStream_t s
 // Returns 0 on success, else a CUresult / -1 (driver entry point missing).
 int encode_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
                         uint64_t stride2, uint32_t box0, uint32_t box1);
+// Same for a 1-byte (e4m3) plane: box0 must be 128 elements (one 128-byte swizzle row).
+int encode_tmap_u8_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
+                      uint64_t stride2, uint32_t box0, uint32_t box1);
 
 }  // namespace s3b

@@ -239,74 +239,93 @@ __device__ __forceinline__ void epi_chunk_coalesced(const GemmParams& p, const E
         if ((er.mask_bits >> it) & 1u) x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.out_f32 != nullptr) *reinterpret_cast<float4*>(p.out_f32 + o) = x;
         if (p.out_hi != nullptr) {
-            uint32_t h0, l0, h1, l1;
-            split_pack2(x.x, x.y, h0, l0);
-            split_pack2(x.z, x.w, h1, l1);
-            *reinterpret_cast<uint2*>(p.out_hi + o) = make_uint2(h0, h1);
-            *reinterpret_cast<uint2*>(p.out_lo + o) = make_uint2(l0, l1);
+            if (p.out_fmt != 0) {
+                store_q8x4(x, p.out_hi, p.out_h8, p.out_l8, o);
+            } else {
+                uint32_t h0, l0, h1, l1;
+                split_pack2(x.x, x.y, h0, l0);
+                split_pack2(x.z, x.w, h1, l1);
+                *reinterpret_cast<uint2*>(p.out_hi + o) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(p.out_lo + o) = make_uint2(l0, l1);
+            }
         }
     }
     __syncwarp();  // the staging buffer is rewritten by the next chunk
 }
 
-// One warp normalises one complete output row (fused LayerNorm of the CTA-pair kernel). Same arithmetic, in the same
-// order, as layernorm_kernel (norm.cu): two-pass statistics held in registers, biased variance, eps 1e-5.
+// One warp normalises complete output rows (fused LayerNorm of the CTA-pair kernel), TWO rows at a time so that the L2
+// round trip of one row's loads overlaps the other row's reductions (a single row per iteration was latency-bound:
+// ~1.7 k cycles per row, which stalled the epilogue warps long enough to starve the accumulator double buffer).
+// Same arithmetic, in the same order, as layernorm_kernel (norm.cu): two-pass statistics held in registers, biased
+// variance, eps 1e-5 — the values are bit-identical to the separate kernel's.
 template <int V4>
-__device__ __forceinline__ void ln_row(const GemmParams& p, size_t row, int lane) {
+__device__ __forceinline__ void ln_rows2(const GemmParams& p, size_t row_a, size_t row_b, bool has_b, int lane) {
     constexpr int D = V4 * 128;
-    const float4* xr = reinterpret_cast<const float4*>(p.out_f32 + row * D);
-    float4 v[V4];
-    float s = 0.f;
+    const float4* xa = reinterpret_cast<const float4*>(p.out_f32 + row_a * D);
+    const float4* xb = reinterpret_cast<const float4*>(p.out_f32 + row_b * D);
+    float4 va[V4], vb[V4];
 #pragma unroll
-    for (int i = 0; i < V4; ++i) {
-        v[i] = __ldcg(xr + lane + 32 * i);  // written by other SMs a moment ago: read through L2
-        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
-    const float mean = warp_sum(s) * (1.0f / D);
-    float q = 0.f;
+    for (int i = 0; i < V4; ++i) va[i] = __ldcg(xa + lane + 32 * i);  // written by other SMs a moment ago: through L2
 #pragma unroll
-    for (int i = 0; i < V4; ++i) {
-        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-        q += (a * a + b * b) + (c * c + d * d);
-    }
-    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+    for (int i = 0; i < V4; ++i) vb[i] = __ldcg(xb + lane + 32 * i);
     const float4* g4 = reinterpret_cast<const float4*>(p.ln_gamma);
     const float4* b4 = reinterpret_cast<const float4*>(p.ln_beta);
 #pragma unroll
-    for (int i = 0; i < V4; ++i) {
-        const int c4 = lane + 32 * i;
-        const float4 g = __ldg(g4 + c4), b = __ldg(b4 + c4);
-        float4 y;
-        y.x = (v[i].x - mean) * rstd * g.x + b.x;
-        y.y = (v[i].y - mean) * rstd * g.y + b.y;
-        y.z = (v[i].z - mean) * rstd * g.z + b.z;
-        y.w = (v[i].w - mean) * rstd * g.w + b.w;
-        if (p.ln_gelu) y.x = gelu_erf(y.x), y.y = gelu_erf(y.y), y.z = gelu_erf(y.z), y.w = gelu_erf(y.w);
-        if (p.ln_out_f32 != nullptr) reinterpret_cast<float4*>(p.ln_out_f32 + row * D)[c4] = y;
-        if (p.ln_out_hi != nullptr) {
-            uint32_t h0, l0, h1, l1;
-            split_pack2(y.x, y.y, h0, l0);
-            split_pack2(y.z, y.w, h1, l1);
-            reinterpret_cast<uint2*>(p.ln_out_hi + row * D)[c4] = make_uint2(h0, h1);
-            reinterpret_cast<uint2*>(p.ln_out_lo + row * D)[c4] = make_uint2(l0, l1);
+    for (int which = 0; which < 2; ++which) {
+        if (which == 1 && !has_b) break;
+        float4(&v)[V4] = which == 0 ? va : vb;
+        const size_t row = which == 0 ? row_a : row_b;
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < V4; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        const float mean = warp_sum(s) * (1.0f / D);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < V4; ++i) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+        const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < V4; ++i) {
+            const int c4 = lane + 32 * i;
+            const float4 g = __ldg(g4 + c4), b = __ldg(b4 + c4);
+            float4 y;
+            y.x = (v[i].x - mean) * rstd * g.x + b.x;
+            y.y = (v[i].y - mean) * rstd * g.y + b.y;
+            y.z = (v[i].z - mean) * rstd * g.z + b.z;
+            y.w = (v[i].w - mean) * rstd * g.w + b.w;
+            if (p.ln_gelu) y.x = gelu_erf(y.x), y.y = gelu_erf(y.y), y.z = gelu_erf(y.z), y.w = gelu_erf(y.w);
+            if (p.ln_out_f32 != nullptr) reinterpret_cast<float4*>(p.ln_out_f32 + row * D)[c4] = y;
+            if (p.ln_out_hi != nullptr && p.out_fmt != 0) {
+                store_q8x4(y, p.ln_out_hi, p.ln_out_h8, p.ln_out_l8, row * D + 4 * (size_t)c4);
+            } else if (p.ln_out_hi != nullptr) {
+                uint32_t h0, l0, h1, l1;
+                split_pack2(y.x, y.y, h0, l0);
+                split_pack2(y.z, y.w, h1, l1);
+                reinterpret_cast<uint2*>(p.ln_out_hi + row * D)[c4] = make_uint2(h0, h1);
+                reinterpret_cast<uint2*>(p.ln_out_lo + row * D)[c4] = make_uint2(l0, l1);
+            }
         }
     }
 }
 
-// 16 of the 128 rows of a finished row block per epilogue warp. Not inlined: its registers (up to 40 for the row) must
-// not push the hot epilogue loop of the GEMM kernel into spills.
+// 16 of the 128 rows of a finished row block per epilogue warp. Not inlined: its registers (two rows) must not push
+// the hot epilogue loop of the GEMM kernel into spills.
 __device__ __noinline__ void ln_tile_rows(const GemmParams* pp, int batch, int row0, int ewarp, int lane) {
     const GemmParams& p = *pp;
     const int r_begin = ewarp * 16;
-    for (int r = r_begin; r < r_begin + 16; ++r) {
-        const int rr = row0 + r;
-        if (rr >= p.rows_per_batch) break;
-        const size_t grow = (size_t)batch * p.out_rows_per_batch + rr;
+    for (int r = r_begin; r < r_begin + 16; r += 2) {
+        const int ra = row0 + r, rb = ra + 1;
+        if (ra >= p.rows_per_batch) break;
+        const bool has_b = rb < p.rows_per_batch;
+        const size_t ga = (size_t)batch * p.out_rows_per_batch + ra;
+        const size_t gb = has_b ? ga + 1 : ga;
         switch (p.ldo) {
-            case 512: ln_row<4>(p, grow, lane); break;
-            case 768: ln_row<6>(p, grow, lane); break;
-            case 1024: ln_row<8>(p, grow, lane); break;
-            default: ln_row<10>(p, grow, lane); break;
+            case 512: ln_rows2<4>(p, ga, gb, has_b, lane); break;
+            case 768: ln_rows2<6>(p, ga, gb, has_b, lane); break;
+            case 1024: ln_rows2<8>(p, ga, gb, has_b, lane); break;
+            default: ln_rows2<10>(p, ga, gb, has_b, lane); break;
         }
     }
 }
@@ -500,8 +519,14 @@ static constexpr int k2SmemBytes = k2Stages * k2StageBytes + 256 + k2EpiWarps * 
 // with four, the GELU + split epilogue of a K=768 tile (fc1, QKV) took longer than its 12 k-blocks of MMAs.
 static constexpr int k2Threads = 384;
 
+// kScheme 0: bf16 hi/lo operands, 3 MMAs per product (k-blocks of 64). kScheme 1 ("f16q8"): per 128-wide k-block one
+// stage of e4m3 correction operands (A_l8 | A_h8 | W_h8 | W_l8: two kind::f8f6f4 MMAs per 32-wide k-step) in a first
+// pass over K, then one stage of fp16 operands (A16[k] | A16[k+64] | W16[k] | W16[k+64]: one kind::f16 MMA per 16-wide
+// k-step) in a second pass — 16 instruction slots per 128 of K instead of 24. The corrections carry the factor
+// 2^kQ8Scale; the first main MMA of the tile scales the accumulator back (scale-input-d).
+template <int kScheme>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
-    gemm2_bf16x3_kernel(const __grid_constant__ GemmParams p) {
+    gemm2_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + k2Stages * k2StageBytes);
@@ -575,31 +600,65 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
                 const int a_k0 = p.a_k_per_ntile * n_tile;
                 const int b_n0 = (p.b_n_tiled ? n_tile * p.umma_n : 0) + (int)rank * (p.umma_n >> 1);
                 const int b_z0 = n_tile * p.b_z_per_ntile;
-                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-                    const int kq = kb / p.kb_per_row;
-                    const int kr = kb - kq * p.kb_per_row;
-                    mbar_wait(&empty_bar[stage], phase ^ 1u);
-                    uint8_t* st = smem + stage * k2StageBytes;
-                    // bytes of both CTAs: 2 x (A_hi + A_lo + two half-B planes of umma_n/2 rows)
-                    if (leader)
-                        mbar_arrive_expect_tx(&full_bar[stage],
-                                              2u * (2u * k2TileBytes + 2u * (uint32_t)(p.umma_n >> 1) * k2BlockK * 2u));
-                    else mbar_arrive_remote(&full_bar[stage], 0);
-                    const int a_row = row0 + kq * p.a_row_step + p.a_row_off;
-                    tma_load_3d_2cta(st, &p.a_hi, &full_bar[stage], a_k0 + kr * k2BlockK, a_row, batch);
-                    tma_load_3d_2cta(st + k2TileBytes, &p.a_lo, &full_bar[stage], a_k0 + kr * k2BlockK, a_row, batch);
-                    const int b_k = (p.b_k_linear ? kb : kr) * k2BlockK;
-                    const int b_z = p.b_k_linear ? 0 : b_z0 + kq;
-                    tma_load_3d_2cta(st + 2 * k2TileBytes, &p.b_hi, &full_bar[stage], b_k, b_n0, b_z);
-                    tma_load_3d_2cta(st + 3 * k2TileBytes, &p.b_lo, &full_bar[stage], b_k, b_n0, b_z);
-                    if (++stage == k2Stages) stage = 0, phase ^= 1u;
+                if constexpr (kScheme == 0) {
+                    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                        const int kq = kb / p.kb_per_row;
+                        const int kr = kb - kq * p.kb_per_row;
+                        mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        uint8_t* st = smem + stage * k2StageBytes;
+                        // bytes of both CTAs: 2 x (A_hi + A_lo + two half-B planes of umma_n/2 rows)
+                        if (leader)
+                            mbar_arrive_expect_tx(&full_bar[stage],
+                                                  2u * (2u * k2TileBytes + 2u * (uint32_t)(p.umma_n >> 1) * k2BlockK * 2u));
+                        else mbar_arrive_remote(&full_bar[stage], 0);
+                        const int a_row = row0 + kq * p.a_row_step + p.a_row_off;
+                        tma_load_3d_2cta(st, &p.a_hi, &full_bar[stage], a_k0 + kr * k2BlockK, a_row, batch);
+                        tma_load_3d_2cta(st + k2TileBytes, &p.a_lo, &full_bar[stage], a_k0 + kr * k2BlockK, a_row, batch);
+                        const int b_k = (p.b_k_linear ? kb : kr) * k2BlockK;
+                        const int b_z = p.b_k_linear ? 0 : b_z0 + kq;
+                        tma_load_3d_2cta(st + 2 * k2TileBytes, &p.b_hi, &full_bar[stage], b_k, b_n0, b_z);
+                        tma_load_3d_2cta(st + 3 * k2TileBytes, &p.b_lo, &full_bar[stage], b_k, b_n0, b_z);
+                        if (++stage == k2Stages) stage = 0, phase ^= 1u;
+                    }
+                } else {
+                    // pass 0: e4m3 correction operands, pass 1: fp16 main operands; 128 elements of K per stage
+                    for (int pass = 0; pass < 2; ++pass) {
+                        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                            const int kq = kb / p.kb_per_row;
+                            const int kr = kb - kq * p.kb_per_row;
+                            mbar_wait(&empty_bar[stage], phase ^ 1u);
+                            uint8_t* st = smem + stage * k2StageBytes;
+                            // both passes move the same bytes: 128 rows x 128 B per A tile, umma_n/2 rows x 128 B per W tile
+                            if (leader)
+                                mbar_arrive_expect_tx(&full_bar[stage],
+                                                      2u * (2u * k2TileBytes + 2u * (uint32_t)(p.umma_n >> 1) * 128u));
+                            else mbar_arrive_remote(&full_bar[stage], 0);
+                            const int a_row = row0 + kq * p.a_row_step + p.a_row_off;
+                            const int a_k = a_k0 + kr * 128;
+                            const int b_k = (p.b_k_linear ? kb : kr) * 128;
+                            const int b_z = p.b_k_linear ? 0 : b_z0 + kq;
+                            if (pass == 0) {
+                                tma_load_3d_2cta(st, &p.a_l8, &full_bar[stage], a_k, a_row, batch);
+                                tma_load_3d_2cta(st + k2TileBytes, &p.a_h8, &full_bar[stage], a_k, a_row, batch);
+                                tma_load_3d_2cta(st + 2 * k2TileBytes, &p.b_h8, &full_bar[stage], b_k, b_n0, b_z);
+                                tma_load_3d_2cta(st + 3 * k2TileBytes, &p.b_l8, &full_bar[stage], b_k, b_n0, b_z);
+                            } else {
+                                tma_load_3d_2cta(st, &p.a_hi, &full_bar[stage], a_k, a_row, batch);
+                                tma_load_3d_2cta(st + k2TileBytes, &p.a_hi, &full_bar[stage], a_k + 64, a_row, batch);
+                                tma_load_3d_2cta(st + 2 * k2TileBytes, &p.b_hi, &full_bar[stage], b_k, b_n0, b_z);
+                                tma_load_3d_2cta(st + 3 * k2TileBytes, &p.b_hi, &full_bar[stage], b_k + 64, b_n0, b_z);
+                            }
+                            if (++stage == k2Stages) stage = 0, phase ^= 1u;
+                        }
+                    }
                 }
             }
         }
     } else if (warp == 1 && leader) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (elect_one()) {
-            const uint32_t idesc = make_idesc_bf16(2 * kBlockM, (uint32_t)p.umma_n);
+            const uint32_t idesc = kScheme == 0 ? make_idesc_bf16(2 * kBlockM, (uint32_t)p.umma_n)
+                                                : make_idesc_f16(2 * kBlockM, (uint32_t)p.umma_n);
             const int k_steps = p.k_steps > 0 ? p.k_steps : k2BlockK / 16;
             int stage = 0;
             uint32_t phase = 0;
@@ -610,26 +669,59 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccCols;
-                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    if (done == 0 && kb == 0) S3B_GTR(3);
-                    const uint32_t st = smem_u32(smem + stage * k2StageBytes);
-                    const uint64_t da_hi = make_smem_desc<128>(st);
-                    const uint64_t da_lo = make_smem_desc<128>(st + k2TileBytes);
-                    const uint64_t db_hi = make_smem_desc<128>(st + 2 * k2TileBytes);
-                    const uint64_t db_lo = make_smem_desc<128>(st + 3 * k2TileBytes);
+                if constexpr (kScheme == 0) {
+                    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        if (done == 0 && kb == 0) S3B_GTR(3);
+                        const uint32_t st = smem_u32(smem + stage * k2StageBytes);
+                        const uint64_t da_hi = make_smem_desc<128>(st);
+                        const uint64_t da_lo = make_smem_desc<128>(st + k2TileBytes);
+                        const uint64_t db_hi = make_smem_desc<128>(st + 2 * k2TileBytes);
+                        const uint64_t db_lo = make_smem_desc<128>(st + 3 * k2TileBytes);
 #pragma unroll
-                    for (int k = 0; k < k2BlockK / 16; ++k) {
-                        if (k < k_steps) {
-                            const uint64_t ko = (uint64_t)(k * 2);
-                            umma_bf16_2cta(d_tmem, da_lo + ko, db_hi + ko, idesc, (kb | k) != 0 ? 1u : 0u);
-                            umma_bf16_2cta(d_tmem, da_hi + ko, db_lo + ko, idesc, 1u);
-                            umma_bf16_2cta(d_tmem, da_hi + ko, db_hi + ko, idesc, 1u);
+                        for (int k = 0; k < k2BlockK / 16; ++k) {
+                            if (k < k_steps) {
+                                const uint64_t ko = (uint64_t)(k * 2);
+                                umma_bf16_2cta(d_tmem, da_lo + ko, db_hi + ko, idesc, (kb | k) != 0 ? 1u : 0u);
+                                umma_bf16_2cta(d_tmem, da_hi + ko, db_lo + ko, idesc, 1u);
+                                umma_bf16_2cta(d_tmem, da_hi + ko, db_hi + ko, idesc, 1u);
+                            }
+                        }
+                        umma_commit_2cta(&empty_bar[stage]);
+                        if (++stage == k2Stages) stage = 0, phase ^= 1u;
+                    }
+                } else {
+                    for (int pass = 0; pass < 2; ++pass) {
+                        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                            mbar_wait(&full_bar[stage], phase);
+                            tc_fence_after();
+                            if (done == 0 && kb == 0 && pass == 0) S3B_GTR(3);
+                            const uint32_t st = smem_u32(smem + stage * k2StageBytes);
+                            // pass 0: A_l8 x W_h8 and A_h8 x W_l8 (K = 32 per MMA, 32 bytes);
+                            // pass 1: A16[k..k+64) x W16[k..k+64) and the next 64 (K = 16 per MMA, 32 bytes)
+                            const uint64_t da0 = make_smem_desc<128>(st), da1 = make_smem_desc<128>(st + k2TileBytes);
+                            const uint64_t db0 = make_smem_desc<128>(st + 2 * k2TileBytes);
+                            const uint64_t db1 = make_smem_desc<128>(st + 3 * k2TileBytes);
+#pragma unroll
+                            for (int t = 0; t < 2; ++t) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const uint64_t ko = (uint64_t)(k * 2);
+                                    const uint64_t da = (t == 0 ? da0 : da1) + ko, db = (t == 0 ? db0 : db1) + ko;
+                                    if (pass == 0) {
+                                        umma_q8_2cta(d_tmem, da, db, idesc, (kb | t | k) != 0 ? 1u : 0u);
+                                    } else if ((kb | t | k) == 0) {
+                                        umma_f16_2cta_scaled(d_tmem, da, db, idesc);  // D = A*B + D * 2^-kQ8Scale
+                                    } else {
+                                        umma_bf16_2cta(d_tmem, da, db, idesc, 1u);  // kind::f16, formats from idesc
+                                    }
+                                }
+                            }
+                            umma_commit_2cta(&empty_bar[stage]);
+                            if (++stage == k2Stages) stage = 0, phase ^= 1u;
                         }
                     }
-                    umma_commit_2cta(&empty_bar[stage]);
-                    if (++stage == k2Stages) stage = 0, phase ^= 1u;
                 }
                 umma_commit_2cta(&tmem_full[acc]);
                 S3B_GTR(4);
@@ -734,12 +826,18 @@ static cudaError_t launch_pair(const GemmParams& p, int sm_count, cudaStream_t s
     bool& attr_set = attr_once.current();
     if (!attr_set) {
         cudaError_t e =
-            cudaFuncSetAttribute(gemm2_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes);
+            cudaFuncSetAttribute(gemm2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(gemm2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     // umma_n / 2 columns per epilogue warp group, in 32-column chunks
-    if ((p.umma_n != 256 && p.umma_n != 192 && p.umma_n != 128) || p.block_k != k2BlockK) return cudaErrorInvalidValue;
+    if (p.umma_n != 256 && p.umma_n != 192 && p.umma_n != 128) return cudaErrorInvalidValue;
+    if (p.scheme == 0 ? p.block_k != k2BlockK : (p.block_k != 128 || p.umma_n == 192 || p.k_steps != 0))
+        return cudaErrorInvalidValue;
+    if (p.out_fmt != 0 && (p.qkv_mode || (p.out_hi != nullptr && (p.out_h8 == nullptr || p.out_l8 == nullptr))))
+        return cudaErrorInvalidValue;
     if (p.ln_gamma != nullptr &&
         (p.out_f32 == nullptr || p.ln_counter == nullptr || p.qkv_mode || p.n_tiles * p.umma_n != p.ldo ||
          (p.ldo != 512 && p.ldo != 768 && p.ldo != 1024 && p.ldo != 1280)))
@@ -747,7 +845,8 @@ static cudaError_t launch_pair(const GemmParams& p, int sm_count, cudaStream_t s
     const int num_pt = p.batches * ((p.tiles_m_per_batch + 1) / 2) * p.n_tiles;
     if (num_pt <= 0) return cudaSuccess;
     const int clusters = num_pt < sm_count / 2 ? num_pt : sm_count / 2;
-    return launch_pdl(gemm2_bf16x3_kernel, dim3(2 * clusters), dim3(k2Threads), k2SmemBytes, stream, p);
+    if (p.scheme != 0) return launch_pdl(gemm2_kernel<1>, dim3(2 * clusters), dim3(k2Threads), k2SmemBytes, stream, p);
+    return launch_pdl(gemm2_kernel<0>, dim3(2 * clusters), dim3(k2Threads), k2SmemBytes, stream, p);
 }
 
 template <int BLOCK_N, int BLOCK_K>
@@ -811,6 +910,22 @@ int encode_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_
     const CUtensorMapSwizzle sw = box0 == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return (int)r;
+}
+
+
+int encode_tmap_u8_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
+                      uint64_t stride2, uint32_t box0, uint32_t box1) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (fn == nullptr) return -1;
+    if (box0 != 128) return -2;  // one 128-byte swizzle row of e4m3 elements
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {stride1, stride2};  // bytes == elements
+    cuuint32_t box[3] = {box0, box1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return (int)r;
 }

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "common.cuh"
+
 namespace s3b {
 
 // ---- frontend.cu ---------------------------------------------------------------------------------
@@ -12,22 +14,23 @@ cudaError_t launch_split(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, s
 cudaError_t launch_wav_pack(const float* const* wavs, const long long* lens, int B, long long Lpad, int normalize,
                             float* mean_rstd_ws, float* out, cudaStream_t s);
 size_t conv0_ws_part_floats(int B, int L0);
+cudaError_t launch_split_q8(const float* x, __nv_bfloat16* p16, uint8_t* h8, uint8_t* l8, size_t n, int weight,
+                            cudaStream_t s);
 cudaError_t launch_conv0_groupnorm(const float* x, int B, long long L, int L0, const float* w, const float* gamma,
-                                   const float* beta, float* ws_part, float* ws_scale_shift, __nv_bfloat16* out_hi,
-                                   __nv_bfloat16* out_lo, cudaStream_t s);
+                                   const float* beta, float* ws_part, float* ws_scale_shift, const OutPlanes& op,
+                                   cudaStream_t s);
 cudaError_t launch_conv0_layernorm(const float* x, int B, long long L, int L0, const float* w, const float* cbias,
-                                   const float* gamma, const float* beta, __nv_bfloat16* out_hi,
-                                   __nv_bfloat16* out_lo, cudaStream_t s);
+                                   const float* gamma, const float* beta, const OutPlanes& op, cudaStream_t s);
 
 // ---- norm.cu -------------------------------------------------------------------------------------
 // y = LayerNorm_D(x) * gamma + beta (eps 1e-5, biased var), optional GELU; D in {512, 768, 1024}.
 // Any of out_f32 / (out_hi,out_lo) may be null. x and out_f32 may alias.
 cudaError_t launch_layernorm(const float* x, size_t M, int D, const float* gamma, const float* beta, int gelu,
-                             float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t s);
+                             float* out_f32, const OutPlanes& op, cudaStream_t s);
 // out[m] = sum_l w[l] * hs[l][m]   (Featurizer._weighted_sum, interfaces.py:217-248; w already softmaxed)
 cudaError_t launch_posconv_combine(const float* z, const float* x, const float* bias, int B, int T, int D, int cpg,
                                    const float* gamma, const float* beta, int do_ln, float* out_f32,
-                                   __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t s);
+                                   const OutPlanes& op, cudaStream_t s);
 cudaError_t launch_weighted_sum(const float* hs, int NL, size_t n_per_layer, const float* w, float* out,
                                 cudaStream_t s);
 // grad_w[l] = sum_m hs[l][m] * gout[m]
@@ -51,7 +54,7 @@ struct AttnParams {
     const float* bias_table;    // [H][bias_stride], entry (h, k - q + bias_center); or null
     int bias_stride, bias_center;
     const float* gate;          // [B][H][T] or null
-    __nv_bfloat16 *ctx_hi, *ctx_lo;  // [B*T][D] split bf16 (A operand of out_proj)
+    OutPlanes ctx;  // [B*T][D] A operand of out_proj, in either operand format
     // optional timeline (debug): clock64 stamps of CTA `trace_block`, [2 roles][16 blocks][8 slots]
     long long* trace;
     int trace_block;

@@ -94,16 +94,30 @@ struct DevBuf {
     }
 };
 
-struct SplitBuf {  // bf16 hi / lo planes
+// One GEMM operand in HBM, 4 bytes per element in either format:
+//   fmt 0 (bf16x3 scheme): `hi` = bf16 hi plane, `lo` = bf16 lo plane
+//   fmt 1 (f16q8 scheme) : `hi` = fp16 plane, `lo` holds the two e4m3 planes back to back (h8 at 0, l8 at l8_off)
+struct SplitBuf {
     DevBuf hi, lo;
+    size_t l8_off = 0;
     int ensure(size_t elems) {
         S3B_OK(hi.ensure(elems * 2));
-        return lo.ensure(elems * 2);
+        const size_t before = lo.bytes;
+        S3B_OK(lo.ensure(elems * 2));
+        if (lo.bytes != before) l8_off = (elems + 255) & ~(size_t)255;
+        return 0;
     }
     __nv_bfloat16* h() const { return hi.as<__nv_bfloat16>(); }
     __nv_bfloat16* l() const { return lo.as<__nv_bfloat16>(); }
-    void release() { hi.release(), lo.release(); }
+    uint8_t* h8() const { return lo.as<uint8_t>(); }
+    uint8_t* l8() const { return lo.as<uint8_t>() + l8_off; }
+    OutPlanes planes(int fmt) const { return OutPlanes{h(), fmt ? nullptr : l(), fmt ? h8() : nullptr, fmt ? l8() : nullptr, fmt}; }
+    void release() { hi.release(), lo.release(), l8_off = 0; }
 };
+
+#ifndef S3B_DEFAULT_SCHEME
+#define S3B_DEFAULT_SCHEME 0
+#endif
 
 static const int kNumConv = 7;
 static const int kConvK[kNumConv] = {10, 3, 3, 3, 3, 2, 2};
@@ -166,6 +180,7 @@ struct s3b_model {
     std::map<std::string, HostTensor> host;
     bool finalized = false;
     int sm_count = 148;
+    int scheme = 0;  // tensor-core operand scheme of the conv / linear GEMMs: 0 = bf16x3, 1 = f16q8 (gemm.cuh)
     Profiler prof;
     long long launches_total = 0;  // kernels launched by this model since creation
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
@@ -195,11 +210,12 @@ static int upload_f32(DevBuf& dst, const float* src, size_t n) {
     CUDA_OK(cudaMemcpy(dst.p, src, n * 4, cudaMemcpyHostToDevice));
     return 0;
 }
-static int upload_split(SplitBuf& dst, const float* src, size_t n) {
+static int upload_split(SplitBuf& dst, const float* src, size_t n, int fmt = 0) {
     DevBuf tmp;
     S3B_OK(upload_f32(tmp, src, n));
     S3B_OK(dst.ensure(n));
-    CUDA_OK(launch_split(tmp.as<float>(), dst.h(), dst.l(), n, 0));
+    if (fmt != 0) CUDA_OK(launch_split_q8(tmp.as<float>(), dst.h(), dst.h8(), dst.l8(), n, 1, 0));
+    else CUDA_OK(launch_split(tmp.as<float>(), dst.h(), dst.l(), n, 0));
     CUDA_OK(cudaDeviceSynchronize());
     tmp.release();
     return 0;
@@ -248,6 +264,14 @@ extern "C" int s3b_device_count(void) {
     return n;
 }
 
+// Operand scheme of the GEMMs: "f16q8" = fp16 product + two e4m3 correction products (2 MMA slots
+// per 16 of K), "bf16x3" = bf16 hi/lo, 3 MMAs. S3B_GEMM_SCHEME overrides the default.
+static int default_scheme() {
+    const char* e = getenv("S3B_GEMM_SCHEME");
+    if (e != nullptr) return (strcmp(e, "f16q8") == 0 || strcmp(e, "1") == 0) ? 1 : 0;
+    return S3B_DEFAULT_SCHEME;
+}
+
 // ------------------------------------------------------------------------------------------------
 // C ABI: model lifetime
 // ------------------------------------------------------------------------------------------------
@@ -263,6 +287,7 @@ extern "C" int s3b_model_create(const s3b_config* cfg, s3b_model** out) {
     if (cfg->num_layers < 1 || cfg->num_layers > 63) return fail("num_layers out of range");
     s3b_model* m = new s3b_model();
     m->cfg = *cfg;
+    m->scheme = default_scheme();
     *out = m;
     return 0;
 }
@@ -353,7 +378,7 @@ extern "C" int s3b_model_finalize(s3b_model* m) {
         for (int o = 0; o < C; ++o)
             for (int ci = 0; ci < C; ++ci)
                 for (int j = 0; j < kw; ++j) r[((size_t)o * kw + j) * C + ci] = t->data[((size_t)o * C + ci) * kw + j];
-        S3B_OK(upload_split(m->conv_w[i], r.data(), r.size()));
+        S3B_OK(upload_split(m->conv_w[i], r.data(), r.size(), m->scheme));
         if (c.conv_bias) S3B_OK(upload_vec(m, p + ".0.bias", C, m->conv_b[i]));
         if (c.extractor_layer_norm) {
             S3B_OK(upload_vec(m, p + ".2.1.weight", C, m->conv_ln_g[i]));
@@ -364,7 +389,7 @@ extern "C" int s3b_model_finalize(s3b_model* m) {
     S3B_OK(upload_vec(m, "layer_norm.weight", C, m->ln512_g));
     S3B_OK(upload_vec(m, "layer_norm.bias", C, m->ln512_b));
     S3B_OK(need(m, "post_extract_proj.weight", {D, C}, &t));
-    S3B_OK(upload_split(m->proj_w, t->data.data(), t->numel()));
+    S3B_OK(upload_split(m->proj_w, t->data.data(), t->numel(), m->scheme));
     S3B_OK(upload_vec(m, "post_extract_proj.bias", D, m->proj_b));
     // ---- pos_conv: fold weight_norm(dim=2): W[o][c][k] = g[k] * v[o][c][k] / ||v[:,:,k]||  ---------------
     //      (make_conv_pos, wav2vec2_model.py:2937-2953). GEMM B operand: [group*Kp + tap][n = cpg][64 (zero padded)]
@@ -426,18 +451,18 @@ extern "C" int s3b_model_finalize(s3b_model* m) {
         memcpy(w.data() + (size_t)2 * D * D, wv->data.data(), (size_t)D * D * 4);
         memcpy(b.data(), bq->data.data(), D * 4), memcpy(b.data() + D, bk->data.data(), D * 4);
         memcpy(b.data() + 2 * D, bv->data.data(), D * 4);
-        S3B_OK(upload_split(L.qkv, w.data(), w.size()));
+        S3B_OK(upload_split(L.qkv, w.data(), w.size(), m->scheme));
         S3B_OK(upload_f32(L.qkv_b, b.data(), b.size()));
         S3B_OK(need(m, p + "self_attn.out_proj.weight", {D, D}, &t));
-        S3B_OK(upload_split(L.out, t->data.data(), t->numel()));
+        S3B_OK(upload_split(L.out, t->data.data(), t->numel(), m->scheme));
         S3B_OK(upload_vec(m, p + "self_attn.out_proj.bias", D, L.out_b));
         S3B_OK(upload_vec(m, p + "self_attn_layer_norm.weight", D, L.ln1_g));
         S3B_OK(upload_vec(m, p + "self_attn_layer_norm.bias", D, L.ln1_b));
         S3B_OK(need(m, p + "fc1.weight", {F, D}, &t));
-        S3B_OK(upload_split(L.fc1, t->data.data(), t->numel()));
+        S3B_OK(upload_split(L.fc1, t->data.data(), t->numel(), m->scheme));
         S3B_OK(upload_vec(m, p + "fc1.bias", F, L.fc1_b));
         S3B_OK(need(m, p + "fc2.weight", {D, F}, &t));
-        S3B_OK(upload_split(L.fc2, t->data.data(), t->numel()));
+        S3B_OK(upload_split(L.fc2, t->data.data(), t->numel(), m->scheme));
         S3B_OK(upload_vec(m, p + "fc2.bias", D, L.fc2_b));
         S3B_OK(upload_vec(m, p + "final_layer_norm.weight", D, L.ln2_g));
         S3B_OK(upload_vec(m, p + "final_layer_norm.bias", D, L.ln2_b));
@@ -525,13 +550,13 @@ struct Epi {
     const uint8_t* row_mask = nullptr;
     int gelu = 0;
     float* out_f32 = nullptr;
-    __nv_bfloat16* out_hi = nullptr;
-    __nv_bfloat16* out_lo = nullptr;
+    OutPlanes op = no_planes();  // GEMM-operand output (either format)
 };
 
 static void set_epi(GemmParams& p, const Epi& e, int ldo) {
     p.bias = e.bias, p.residual = e.residual, p.row_mask = e.row_mask, p.gelu = e.gelu;
-    p.out_f32 = e.out_f32, p.out_hi = e.out_hi, p.out_lo = e.out_lo, p.ldo = ldo;
+    p.out_f32 = e.out_f32, p.out_hi = e.op.hi, p.out_lo = e.op.lo, p.out_h8 = e.op.h8, p.out_l8 = e.op.l8;
+    p.out_fmt = e.op.fmt, p.ldo = ldo;
     p.qkv_mode = 0;
 }
 
@@ -560,7 +585,7 @@ static int g_force_pair_un = 0;  // s3b_gemm_bench: force the pair-tile width (t
 //   cost = t_mma + (rounds - 1) x max(t_mma, t_epi) + t_epi.
 // What it changes vs the round-1 rule: at the token counts of the sharded runs (M = 1 000 ... 8 000) the exposed
 // epilogue of the last 256-wide tile costs more than a second round of 128-wide tiles (QKV / fc1: -9 ... -11 %).
-static int pick_pair_umma_n(int64_t M, int N, int K, int epi_kind, int sm_count) {
+static int pick_pair_umma_n(int64_t M, int N, int K, int epi_kind, int sm_count, int scheme = 0) {
     if (g_force_pair_un != 0 && N % g_force_pair_un == 0) return g_force_pair_un;
     if (N % 256 != 0) return (N % 128 == 0) ? 128 : 0;
     const int clusters = sm_count / 2 > 0 ? sm_count / 2 : 1;
@@ -571,7 +596,8 @@ static int pick_pair_umma_n(int64_t M, int N, int K, int epi_kind, int sm_count)
     for (int un = 256; un >= 128; un -= 128) {
         const int64_t tiles = pairs * (N / un);
         const int64_t rounds = (tiles + clusters - 1) / clusters;
-        const double t_mma = (double)K * 12.0 * (un / 128) * (un == 128 ? 1.15 : 1.0);
+        // 3 MMA slots per 16 of K (bf16x3) or 2 (f16q8: one fp16 MMA + two e4m3 MMAs that each cover 32 of K)
+        const double t_mma = (double)K * (scheme ? 8.0 : 12.0) * (un / 128) * (un == 128 ? 1.15 : 1.0);
         const double t_epi = epi128 * (un / 128);
         const double cost = t_mma + (double)(rounds - 1) * (t_mma > t_epi ? t_mma : t_epi) + t_epi;
         if (cost < best_cost - 1e-9) best_cost = cost, best = un;
@@ -596,25 +622,36 @@ static int pick_umma_n(int N) {
 
 // out[M][N] = A[M][K] * W[N][K]^T, flat token-major A (hi/lo planes), K % 64 == 0
 // epi_kind: 0 = fp32 output, 1 = bf16 hi/lo output (QKV scatter included), 2 = GELU + hi/lo (tile-width choice only)
-static int linear_params(GemmParams& p, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo,
-                         const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int64_t M, int N, int K,
-                         int epi_kind = 0) {
+// scheme 1: A and W are f16q8 operands (SplitBuf fmt 1), K % 128 == 0.
+static int linear_params(GemmParams& p, const SplitBuf& A, const SplitBuf& W, int64_t M, int N, int K, int epi_kind = 0,
+                         int scheme = 0) {
     memset(&p, 0, sizeof(p));
     if (K % 64 != 0 || N % 16 != 0)  // K % 64 keeps both k-block widths legal
         return fail("linear: K %% 64 or N %% 16 violated (N=%d K=%d)", N, K);
     int un = pick_umma_n(N);
-    if (pairs_enabled() && pick_pair_umma_n(M, N, K, epi_kind, g_sm_count) != 0)
-        un = pick_pair_umma_n(M, N, K, epi_kind, g_sm_count);
+    if (pairs_enabled() && pick_pair_umma_n(M, N, K, epi_kind, g_sm_count, scheme) != 0)
+        un = pick_pair_umma_n(M, N, K, epi_kind, g_sm_count, scheme);
     const int pair = use_cta_pairs(un);
-    const int bk = pair ? 64 : gemm_block_k(un);
-    const int bbox = pair ? un / 2 : un;  // CTA pairs: each CTA loads half of the tile's W rows
-    TMAP_OK(encode_tmap_bf16_3d(&p.a_hi, a_hi, K, M, 1, K, (uint64_t)M * K, bk, 128));
-    TMAP_OK(encode_tmap_bf16_3d(&p.a_lo, a_lo, K, M, 1, K, (uint64_t)M * K, bk, 128));
-    TMAP_OK(encode_tmap_bf16_3d(&p.b_hi, w_hi, K, N, 1, K, (uint64_t)N * K, bk, bbox));
-    TMAP_OK(encode_tmap_bf16_3d(&p.b_lo, w_lo, K, N, 1, K, (uint64_t)N * K, bk, bbox));
-    p.two_cta = pair;
+    if (scheme != 0) {
+        if (!pair || K % 128 != 0) return fail("f16q8 GEMM needs CTA pairs and K %% 128 == 0 (N=%d K=%d)", N, K);
+        TMAP_OK(encode_tmap_bf16_3d(&p.a_hi, A.h(), K, M, 1, K, (uint64_t)M * K, 64, 128));
+        TMAP_OK(encode_tmap_u8_3d(&p.a_h8, A.h8(), K, M, 1, K, (uint64_t)M * K, 128, 128));
+        TMAP_OK(encode_tmap_u8_3d(&p.a_l8, A.l8(), K, M, 1, K, (uint64_t)M * K, 128, 128));
+        TMAP_OK(encode_tmap_bf16_3d(&p.b_hi, W.h(), K, N, 1, K, (uint64_t)N * K, 64, un / 2));
+        TMAP_OK(encode_tmap_u8_3d(&p.b_h8, W.h8(), K, N, 1, K, (uint64_t)N * K, 128, un / 2));
+        TMAP_OK(encode_tmap_u8_3d(&p.b_l8, W.l8(), K, N, 1, K, (uint64_t)N * K, 128, un / 2));
+        p.scheme = 1, p.two_cta = 1, p.block_k = 128, p.num_k_blocks = K / 128, p.kb_per_row = K / 128;
+    } else {
+        const int bk = pair ? 64 : gemm_block_k(un);
+        const int bbox = pair ? un / 2 : un;  // CTA pairs: each CTA loads half of the tile's W rows
+        TMAP_OK(encode_tmap_bf16_3d(&p.a_hi, A.h(), K, M, 1, K, (uint64_t)M * K, bk, 128));
+        TMAP_OK(encode_tmap_bf16_3d(&p.a_lo, A.l(), K, M, 1, K, (uint64_t)M * K, bk, 128));
+        TMAP_OK(encode_tmap_bf16_3d(&p.b_hi, W.h(), K, N, 1, K, (uint64_t)N * K, bk, bbox));
+        TMAP_OK(encode_tmap_bf16_3d(&p.b_lo, W.l(), K, N, 1, K, (uint64_t)N * K, bk, bbox));
+        p.two_cta = pair, p.block_k = bk, p.num_k_blocks = K / bk, p.kb_per_row = K / bk;
+    }
     p.batches = 1, p.rows_per_batch = (int)M, p.tiles_m_per_batch = (int)((M + 127) / 128);
-    p.n_tiles = N / un, p.umma_n = un, p.block_k = bk, p.num_k_blocks = K / bk, p.kb_per_row = K / bk;
+    p.n_tiles = N / un, p.umma_n = un;
     p.a_row_step = 0, p.a_row_off = 0, p.a_k_per_ntile = 0, p.b_n_tiled = 1, p.b_z_per_ntile = 0;
     p.out_rows_per_batch = (int)M;
     p.alg_flops = 2.0 * (double)M * N * K;
@@ -623,22 +660,33 @@ static int linear_params(GemmParams& p, const __nv_bfloat16* a_hi, const __nv_bf
 
 // conv i (k in {2,3}, stride 2) over channels-last [B][Lin][512]: row t of the [ceil(Lin/2)][1024] view holds
 // samples (2t, 2t+1); taps 0,1 come from view row t, tap 2 from the first half of view row t+1.
-static int conv_params(GemmParams& p, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const __nv_bfloat16* w_hi,
-                       const __nv_bfloat16* w_lo, int B, int64_t Lin, int64_t Lout, int kw) {
+static int conv_params(GemmParams& p, const SplitBuf& A, const SplitBuf& W, int B, int64_t Lin, int64_t Lout, int kw,
+                       int scheme = 0) {
     memset(&p, 0, sizeof(p));
     const int C = kConvDim, K = kw * C;
     const uint64_t rows = (uint64_t)((Lin + 1) / 2);
     const int pair = use_cta_pairs(256);
-    const int bk = pair ? 64 : gemm_block_k(256);
-    const int bbox = pair ? 128 : 256;
-    TMAP_OK(encode_tmap_bf16_3d(&p.a_hi, a_hi, 2 * C, rows, B, 2 * C, (uint64_t)Lin * C, bk, 128));
-    TMAP_OK(encode_tmap_bf16_3d(&p.a_lo, a_lo, 2 * C, rows, B, 2 * C, (uint64_t)Lin * C, bk, 128));
-    // weights [512][K], K index = tap*512 + channel, read linearly along K
-    TMAP_OK(encode_tmap_bf16_3d(&p.b_hi, w_hi, K, C, 1, K, (uint64_t)C * K, bk, bbox));
-    TMAP_OK(encode_tmap_bf16_3d(&p.b_lo, w_lo, K, C, 1, K, (uint64_t)C * K, bk, bbox));
-    p.two_cta = pair;
+    if (scheme != 0) {
+        if (!pair) return fail("f16q8 GEMM needs CTA pairs");
+        TMAP_OK(encode_tmap_bf16_3d(&p.a_hi, A.h(), 2 * C, rows, B, 2 * C, (uint64_t)Lin * C, 64, 128));
+        TMAP_OK(encode_tmap_u8_3d(&p.a_h8, A.h8(), 2 * C, rows, B, 2 * C, (uint64_t)Lin * C, 128, 128));
+        TMAP_OK(encode_tmap_u8_3d(&p.a_l8, A.l8(), 2 * C, rows, B, 2 * C, (uint64_t)Lin * C, 128, 128));
+        TMAP_OK(encode_tmap_bf16_3d(&p.b_hi, W.h(), K, C, 1, K, (uint64_t)C * K, 64, 128));
+        TMAP_OK(encode_tmap_u8_3d(&p.b_h8, W.h8(), K, C, 1, K, (uint64_t)C * K, 128, 128));
+        TMAP_OK(encode_tmap_u8_3d(&p.b_l8, W.l8(), K, C, 1, K, (uint64_t)C * K, 128, 128));
+        p.scheme = 1, p.two_cta = 1, p.block_k = 128, p.num_k_blocks = K / 128, p.kb_per_row = (2 * C) / 128;
+    } else {
+        const int bk = pair ? 64 : gemm_block_k(256);
+        const int bbox = pair ? 128 : 256;
+        TMAP_OK(encode_tmap_bf16_3d(&p.a_hi, A.h(), 2 * C, rows, B, 2 * C, (uint64_t)Lin * C, bk, 128));
+        TMAP_OK(encode_tmap_bf16_3d(&p.a_lo, A.l(), 2 * C, rows, B, 2 * C, (uint64_t)Lin * C, bk, 128));
+        // weights [512][K], K index = tap*512 + channel, read linearly along K
+        TMAP_OK(encode_tmap_bf16_3d(&p.b_hi, W.h(), K, C, 1, K, (uint64_t)C * K, bk, bbox));
+        TMAP_OK(encode_tmap_bf16_3d(&p.b_lo, W.l(), K, C, 1, K, (uint64_t)C * K, bk, bbox));
+        p.two_cta = pair, p.block_k = bk, p.num_k_blocks = K / bk, p.kb_per_row = (2 * C) / bk;
+    }
     p.batches = B, p.rows_per_batch = (int)Lout, p.tiles_m_per_batch = (int)((Lout + 127) / 128);
-    p.n_tiles = C / 256, p.umma_n = 256, p.block_k = bk, p.num_k_blocks = K / bk, p.kb_per_row = (2 * C) / bk;
+    p.n_tiles = C / 256, p.umma_n = 256;
     p.a_row_step = 1, p.a_row_off = 0, p.a_k_per_ntile = 0, p.b_n_tiled = 1, p.b_z_per_ntile = 0, p.b_k_linear = 1;
     p.out_rows_per_batch = (int)Lout;
     p.alg_flops = 2.0 * (double)B * Lout * C * K;
@@ -721,13 +769,20 @@ static inline void prof_end(s3b_model* m, cudaStream_t st, int cat, int nkernels
 #define KMISC(expr) KLAUNCH(CAT_MISC, 1, 0.0, expr)
 
 // LayerNorm fused into the producing GEMM (gemm.cuh: ln_*): on unless S3B_FUSE_LN=0 (kept for A/B measurements)
-static bool fuse_ln_enabled() {
+// S3B_FUSE_LN: 0 = never, 1 = wherever possible, unset = only where the tile's MMAs (K >= 2048: fc2) leave the epilogue
+// warps the slack to do it (measured, profiles/r2d: fusing behind the K = 768 out_proj made its tiles epilogue-bound)
+static int fuse_ln_mode() {
     const char* e = getenv("S3B_FUSE_LN");  // read per call: tests toggle it (the plan cache is keyed on it)
-    return !(e != nullptr && e[0] == '0') && pairs_enabled();
+    if (!pairs_enabled()) return 0;
+    if (e == nullptr) return 2;
+    return e[0] == '0' ? 0 : 1;
 }
-static void set_ln(GemmParams& p, const float* gamma, const float* beta, int gelu, float* out_f32, __nv_bfloat16* hi,
-                   __nv_bfloat16* lo, unsigned int* counter) {
-    p.ln_gamma = gamma, p.ln_beta = beta, p.ln_gelu = gelu, p.ln_out_f32 = out_f32, p.ln_out_hi = hi, p.ln_out_lo = lo;
+// (the fused LayerNorm's operand output uses the GEMM's out_fmt: callers keep both in the same format)
+static void set_ln(GemmParams& p, const float* gamma, const float* beta, int gelu, float* out_f32, const OutPlanes& op,
+                   unsigned int* counter) {
+    p.ln_gamma = gamma, p.ln_beta = beta, p.ln_gelu = gelu, p.ln_out_f32 = out_f32;
+    p.ln_out_hi = op.hi, p.ln_out_lo = op.lo, p.ln_out_h8 = op.h8, p.ln_out_l8 = op.l8;
+    if (op.hi != nullptr) p.out_fmt = op.fmt;
     p.ln_counter = counter;
 }
 
@@ -746,7 +801,7 @@ struct Plan {
     int B = 0;
     int64_t Lmax = 0;
     uint64_t gen = 0;
-    bool fuse_ln = false;
+    int fuse_ln = 0;
     GemmParams conv[kNumConv];
     GemmParams proj, pos;
     std::vector<LayerPlan> layers;
@@ -800,7 +855,7 @@ struct Fwd {
     long long* d_lens = nullptr;
     int* d_kv = nullptr;
     uint8_t* d_mask = nullptr;
-    bool fuse_ln = false;
+    int fuse_ln = 0;  // fuse_ln_mode()
     unsigned int* cnt[2] = {nullptr, nullptr};  // two alternating row-block counter arrays of the fused LayerNorm
 
     int num_stages() const { return 9 + 5 * m->cfg.num_layers; }
@@ -883,7 +938,7 @@ int Fwd::prepare() {
     S3B_OK(w->h_s.ensure((size_t)M * F));
     if (posconv4_ok(c)) S3B_OK(w->pos_z.ensure((size_t)B * (T + 3) * 4 * D * sizeof(float)));
     if (c.relative_position) S3B_OK(w->gate.ensure((size_t)B * H * T * 4));
-    fuse_ln = fuse_ln_enabled();
+    fuse_ln = fuse_ln_mode();
     {
         const size_t n_cnt = (size_t)B * (L[1] / 128 + 2) + (size_t)M / 128 + 16;
         S3B_OK(w->ln_counters.ensure(2 * n_cnt * sizeof(unsigned int)));
@@ -925,8 +980,7 @@ int Fwd::build_plan(Plan& pl) {
     const int D = c.embed_dim, F = c.ffn_dim, H = c.num_heads, NL = c.num_layers, C = kConvDim;
     for (int i = 1; i < kNumConv; ++i) {
         GemmParams& p = pl.conv[i];
-        S3B_OK(conv_params(p, w->act[i - 1].h(), w->act[i - 1].l(), m->conv_w[i].h(), m->conv_w[i].l(), B, L[i - 1],
-                           L[i], kConvK[i]));
+        S3B_OK(conv_params(p, w->act[i - 1], m->conv_w[i], B, L[i - 1], L[i], kConvK[i], m->scheme));
         Epi e;
         e.bias = c.conv_bias ? m->conv_b[i].as<float>() : nullptr;
         const bool last = (i == kNumConv - 1);
@@ -935,21 +989,21 @@ int Fwd::build_plan(Plan& pl) {
         } else {
             e.gelu = 1;
             if (last) e.out_f32 = w->conv_f32.as<float>();
-            else e.out_hi = w->act[i].h(), e.out_lo = w->act[i].l();
+            else e.op = w->act[i].planes(m->scheme);
         }
         set_epi(p, e, C);
-        if (c.extractor_layer_norm && fuse_ln && p.two_cta)  // per-frame LayerNorm(512) + GELU (wav2vec2_model.py:2887-2897)
+        if (c.extractor_layer_norm && fuse_ln == 1 && p.two_cta)  // per-frame LayerNorm(512) + GELU (wav2vec2_model.py:2887-2897)
             set_ln(p, m->conv_ln_g[i].as<float>(), m->conv_ln_b[i].as<float>(), 1, last ? w->conv_f32.as<float>() : nullptr,
-                   last ? nullptr : w->act[i].h(), last ? nullptr : w->act[i].l(), cnt[i & 1]);
+                   last ? no_planes() : w->act[i].planes(m->scheme), cnt[i & 1]);
     }
     {
         GemmParams& p = pl.proj;
-        S3B_OK(linear_params(p, w->ln512_s.h(), w->ln512_s.l(), m->proj_w.h(), m->proj_w.l(), M, D, C, 1));
+        S3B_OK(linear_params(p, w->ln512_s, m->proj_w, M, D, C, 1, m->scheme));
         Epi e;
         e.bias = m->proj_b.as<float>();
         e.row_mask = d_mask;  // x[padding_mask] = 0 (wav2vec2_model.py:3061-3062)
         e.out_f32 = w->x_f32.as<float>();
-        e.out_hi = w->x_s.h(), e.out_lo = w->x_s.l();
+        e.op = w->x_s.planes(0);  // operand of pos_conv, which stays on the bf16x3 kernel (48-channel groups)
         set_epi(p, e, D);
     }
     {
@@ -976,7 +1030,7 @@ int Fwd::build_plan(Plan& pl) {
         LayerPlan& lp = pl.layers[l];
         {   // QKV projection, scattered per head; q pre-scaled by head_dim^-0.5 (exact power of two) and log2(e)
             GemmParams& p = lp.qkv;
-            S3B_OK(linear_params(p, w->xs_s.h(), w->xs_s.l(), W.qkv.h(), W.qkv.l(), M, 3 * D, D, 1));
+            S3B_OK(linear_params(p, w->xs_s, W.qkv, M, 3 * D, D, 1, m->scheme));
             Epi e;
             e.bias = W.qkv_b.as<float>();
             set_epi(p, e, 3 * D);
@@ -1000,35 +1054,35 @@ int Fwd::build_plan(Plan& pl) {
                 ap.bias_stride = 2 * m->rel_table_T - 1, ap.bias_center = m->rel_table_T - 1;
                 ap.gate = w->gate.as<float>();
             }
-            ap.ctx_hi = w->ctx_s.h(), ap.ctx_lo = w->ctx_s.l();
+            ap.ctx = w->ctx_s.planes(m->scheme);
         }
         {   // out_proj + residual (residual = hidden state l, patched per call)
             GemmParams& p = lp.out;
-            S3B_OK(linear_params(p, w->ctx_s.h(), w->ctx_s.l(), W.out.h(), W.out.l(), M, D, D));
+            S3B_OK(linear_params(p, w->ctx_s, W.out, M, D, D, 0, m->scheme));
             Epi e;
             e.bias = W.out_b.as<float>();
             e.out_f32 = c.layer_norm_first ? w->x1_f32.as<float>() : w->tmp_f32.as<float>();
             set_epi(p, e, D);
-            if (fuse_ln && p.two_cta) {
+            if (fuse_ln == 1 && p.two_cta) {
                 if (c.layer_norm_first)  // x1_s = LN2(r1), r1 = x1_f32
-                    set_ln(p, W.ln2_g.as<float>(), W.ln2_b.as<float>(), 0, nullptr, w->x1_s.h(), w->x1_s.l(), cnt[0]);
+                    set_ln(p, W.ln2_g.as<float>(), W.ln2_b.as<float>(), 0, nullptr, w->x1_s.planes(m->scheme), cnt[0]);
                 else  // x1 = LN1(x + attn)
-                    set_ln(p, W.ln1_g.as<float>(), W.ln1_b.as<float>(), 0, w->x1_f32.as<float>(), w->x1_s.h(), w->x1_s.l(),
-                           cnt[0]);
+                    set_ln(p, W.ln1_g.as<float>(), W.ln1_b.as<float>(), 0, w->x1_f32.as<float>(),
+                           w->x1_s.planes(m->scheme), cnt[0]);
             }
         }
         {   // fc1 + GELU
             GemmParams& p = lp.fc1;
-            S3B_OK(linear_params(p, w->x1_s.h(), w->x1_s.l(), W.fc1.h(), W.fc1.l(), M, F, D, 2));
+            S3B_OK(linear_params(p, w->x1_s, W.fc1, M, F, D, 2, m->scheme));
             Epi e;
             e.bias = W.fc1_b.as<float>();
             e.gelu = 1;
-            e.out_hi = w->h_s.h(), e.out_lo = w->h_s.l();
+            e.op = w->h_s.planes(m->scheme);
             set_epi(p, e, F);
         }
         {   // fc2 + residual (output patched per call for pre-LN models)
             GemmParams& p = lp.fc2;
-            S3B_OK(linear_params(p, w->h_s.h(), w->h_s.l(), W.fc2.h(), W.fc2.l(), M, D, F));
+            S3B_OK(linear_params(p, w->h_s, W.fc2, M, D, F, 0, m->scheme));
             Epi e;
             e.bias = W.fc2_b.as<float>();
             e.residual = w->x1_f32.as<float>();
@@ -1037,13 +1091,13 @@ int Fwd::build_plan(Plan& pl) {
             if (fuse_ln && p.two_cta) {
                 const bool last = (l == NL - 1);
                 if (!c.layer_norm_first)  // hidden state l+1 = LN2(x1 + ffn) (fp32 output patched per call) + operand of layer l+1
-                    set_ln(p, W.ln2_g.as<float>(), W.ln2_b.as<float>(), 0, nullptr, last ? nullptr : w->xs_s.h(),
-                           last ? nullptr : w->xs_s.l(), cnt[1]);
+                    set_ln(p, W.ln2_g.as<float>(), W.ln2_b.as<float>(), 0, nullptr,
+                           last ? no_planes() : w->xs_s.planes(m->scheme), cnt[1]);
                 else if (last)  // encoder.layer_norm on the final output (wav2vec2_model.py:3049-3050), output patched per call
-                    set_ln(p, m->enc_ln_g.as<float>(), m->enc_ln_b.as<float>(), 0, nullptr, nullptr, nullptr, cnt[1]);
+                    set_ln(p, m->enc_ln_g.as<float>(), m->enc_ln_b.as<float>(), 0, nullptr, no_planes(), cnt[1]);
                 else  // pre-LN: the NEXT layer's LN1 of the residual stream this GEMM produces
                     set_ln(p, m->layers[l + 1].ln1_g.as<float>(), m->layers[l + 1].ln1_b.as<float>(), 0, nullptr,
-                           w->xs_s.h(), w->xs_s.l(), cnt[1]);
+                           w->xs_s.planes(m->scheme), cnt[1]);
             }
         }
     }
@@ -1068,13 +1122,13 @@ int Fwd::stage(int s) {
         if (c.extractor_layer_norm) {
             KCONV0(1, launch_conv0_layernorm(w->wav_pad.as<float>(), B, Lmax, (int)L[0], m->conv0_w.as<float>(),
                                              c.conv_bias ? m->conv0_b.as<float>() : nullptr, m->norm0_g.as<float>(),
-                                             m->norm0_b.as<float>(), w->act[0].h(), w->act[0].l(), st));
+                                             m->norm0_b.as<float>(), w->act[0].planes(m->scheme), st));
         } else {
             // a conv-0 bias (conv_bias with extractor_mode "default") is removed again by the per-channel GroupNorm
             // mean: it cancels exactly in (z + b) - mean(z + b), so the kernel never adds it
             KCONV0(3, launch_conv0_groupnorm(w->wav_pad.as<float>(), B, Lmax, (int)L[0], m->conv0_w.as<float>(),
                                              m->norm0_g.as<float>(), m->norm0_b.as<float>(), w->c0_part.as<float>(),
-                                             w->c0_ss.as<float>(), w->act[0].h(), w->act[0].l(), st));
+                                             w->c0_ss.as<float>(), w->act[0].planes(m->scheme), st));
         }
         return 0;
     }
@@ -1087,14 +1141,14 @@ int Fwd::stage(int s) {
             const bool last = (i == kNumConv - 1);
             KNORM(launch_layernorm(w->conv_f32.as<float>(), (size_t)B * L[i], C, m->conv_ln_g[i].as<float>(),
                                    m->conv_ln_b[i].as<float>(), 1, last ? w->conv_f32.as<float>() : nullptr,
-                                   last ? nullptr : w->act[i].h(), last ? nullptr : w->act[i].l(), st));
+                                   last ? no_planes() : w->act[i].planes(m->scheme), st));
         }
         return 0;
     }
     if (s == 7) {
         // ---- LayerNorm(512) -> post_extract_proj (+ zero padded frames) --------------------------------------------
         KNORM(launch_layernorm(w->conv_f32.as<float>(), (size_t)M, C, m->ln512_g.as<float>(), m->ln512_b.as<float>(),
-                               0, nullptr, w->ln512_s.h(), w->ln512_s.l(), st));
+                               0, nullptr, w->ln512_s.planes(m->scheme), st));
         GemmParams p = plan->proj;
         KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
         return 0;
@@ -1108,13 +1162,13 @@ int Fwd::stage(int s) {
             const bool ln = !c.layer_norm_first;
             KNORM(launch_posconv_combine(w->pos_z.as<float>(), w->x_f32.as<float>(), m->pos_b.as<float>(), B, T, D,
                                          D / c.pos_conv_groups, m->enc_ln_g.as<float>(), m->enc_ln_b.as<float>(),
-                                         ln ? 1 : 0, hs0, ln ? w->xs_s.h() : nullptr, ln ? w->xs_s.l() : nullptr, st));
+                                         ln ? 1 : 0, hs0, ln ? w->xs_s.planes(m->scheme) : no_planes(), st));
         } else {
             if (c.layer_norm_first) p.out_f32 = hs0;
             KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
             if (!c.layer_norm_first)
                 KNORM(launch_layernorm(w->tmp_f32.as<float>(), (size_t)M, D, m->enc_ln_g.as<float>(),
-                                       m->enc_ln_b.as<float>(), 0, hs0, w->xs_s.h(), w->xs_s.l(), st));
+                                       m->enc_ln_b.as<float>(), 0, hs0, w->xs_s.planes(m->scheme), st));
         }
         if (layer_done) S3B_OK(layer_done(m, 0, st, user));
         return 0;
@@ -1134,11 +1188,11 @@ int Fwd::stage(int s) {
             // pre-LN: xs = LN1(residual stream); from layer 1 on it is produced by the previous layer's fc2 epilogue
             if (c.layer_norm_first && (l == 0 || plan->layers[l - 1].fc2.ln_gamma == nullptr))
                 KNORM(launch_layernorm(hs_in, (size_t)M, D, W.ln1_g.as<float>(), W.ln1_b.as<float>(), 0, nullptr,
-                                       w->xs_s.h(), w->xs_s.l(), st));
+                                       w->xs_s.planes(m->scheme), st));
             GemmParams p = lp.qkv;
             KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
             if (rel)  // gate from the layer's attention input (post-LN: hs_in; pre-LN: LN1 output) modules.py:534-551
-                KMISC(launch_wavlm_gate(w->xs_s.h(), w->xs_s.l(), (size_t)M, B, T, H, D,
+                KMISC(launch_wavlm_gate(w->xs_s.planes(m->scheme), (size_t)M, B, T, H, D,
                                         c.gru_rel_pos ? W.grep_w.as<float>() : nullptr, W.grep_b.as<float>(),
                                         W.grep_a.as<float>(), w->gate.as<float>(), st));
             return 0;
@@ -1154,10 +1208,10 @@ int Fwd::stage(int s) {
             if (p.ln_gamma != nullptr) return 0;  // LayerNorm fused into the GEMM
             if (c.layer_norm_first)  // x1_s = LN2(r1), r1 = x1_f32
                 KNORM(launch_layernorm(w->x1_f32.as<float>(), (size_t)M, D, W.ln2_g.as<float>(), W.ln2_b.as<float>(), 0,
-                                       nullptr, w->x1_s.h(), w->x1_s.l(), st));
+                                       nullptr, w->x1_s.planes(m->scheme), st));
             else  // x1 = LN1(x + attn)
                 KNORM(launch_layernorm(w->tmp_f32.as<float>(), (size_t)M, D, W.ln1_g.as<float>(), W.ln1_b.as<float>(), 0,
-                                       w->x1_f32.as<float>(), w->x1_s.h(), w->x1_s.l(), st));
+                                       w->x1_f32.as<float>(), w->x1_s.planes(m->scheme), st));
             return 0;
         }
         case 3: {
@@ -1180,10 +1234,10 @@ int Fwd::stage(int s) {
             if (c.layer_norm_first) {
                 if (last)  // encoder.layer_norm on the final output (wav2vec2_model.py:3049-3050)
                     KNORM(launch_layernorm(unnorm, (size_t)M, D, m->enc_ln_g.as<float>(), m->enc_ln_b.as<float>(), 0,
-                                           hs_out, nullptr, nullptr, st));
+                                           hs_out, no_planes(), st));
             } else {
                 KNORM(launch_layernorm(w->tmp_f32.as<float>(), (size_t)M, D, W.ln2_g.as<float>(), W.ln2_b.as<float>(), 0,
-                                       hs_out, last ? nullptr : w->xs_s.h(), last ? nullptr : w->xs_s.l(), st));
+                                       hs_out, last ? no_planes() : w->xs_s.planes(m->scheme), st));
             }
             if (layer_done) S3B_OK(layer_done(m, l + 1, st, user));
             return 0;
@@ -1532,10 +1586,18 @@ extern "C" int s3b_linear_f32(const float* a, const float* w, const float* bias,
     SplitBuf as, ws;
     S3B_OK(as.ensure((size_t)M * K));
     S3B_OK(ws.ensure((size_t)N * K));
-    CUDA_OK(launch_split(a, as.h(), as.l(), (size_t)M * K, st));
-    CUDA_OK(launch_split(w, ws.h(), ws.l(), (size_t)N * K, st));
+    // the operand scheme under test: S3B_GEMM_SCHEME (like a model would pick it), bf16x3 when f16q8 cannot apply
+    int scheme = default_scheme();
+    if (K % 128 != 0 || N % 128 != 0 || !pairs_enabled()) scheme = 0;
+    if (scheme != 0) {
+        CUDA_OK(launch_split_q8(a, as.h(), as.h8(), as.l8(), (size_t)M * K, 0, st));
+        CUDA_OK(launch_split_q8(w, ws.h(), ws.h8(), ws.l8(), (size_t)N * K, 1, st));
+    } else {
+        CUDA_OK(launch_split(a, as.h(), as.l(), (size_t)M * K, st));
+        CUDA_OK(launch_split(w, ws.h(), ws.l(), (size_t)N * K, st));
+    }
     GemmParams p;
-    int r = linear_params(p, as.h(), as.l(), ws.h(), ws.l(), M, N, K);
+    int r = linear_params(p, as, ws, M, N, K, 0, scheme);
     if (r == 0) {
         Epi e;
         e.bias = bias, e.residual = residual, e.gelu = gelu, e.out_f32 = out;
@@ -1595,12 +1657,14 @@ extern "C" int s3b_gemm_bench(int64_t M, int32_t N, int32_t K, int32_t gelu, int
     CUDA_OK(cudaMemset(ws.hi.p, 0x3c, (size_t)N * K * 2));
     GemmParams p;
     g_force_pair_un = force_un;
-    int r = linear_params(p, as.h(), as.l(), ws.h(), ws.l(), M, N, K, gelu ? 2 : 0);
+    int scheme = default_scheme();
+    if (K % 128 != 0 || N % 128 != 0 || !pairs_enabled()) scheme = 0;
+    int r = linear_params(p, as, ws, M, N, K, gelu ? 2 : 0, scheme);
     g_force_pair_un = 0;
     if (r == 0) {
         Epi e;
         e.bias = bias.as<float>();
-        if (gelu) e.gelu = 1, e.out_hi = os.h(), e.out_lo = os.l();
+        if (gelu) e.gelu = 1, e.op = os.planes(scheme);
         else e.residual = res.as<float>(), e.out_f32 = out.as<float>();
         set_epi(p, e, N);
         cudaEvent_t e0, e1;
@@ -1624,7 +1688,7 @@ extern "C" int s3b_gemm_bench(int64_t M, int32_t N, int32_t K, int32_t gelu, int
 extern "C" int s3b_layernorm_f32(const float* x, int64_t M, int32_t D, const float* gamma, const float* beta,
                                  int32_t gelu, float* out, void* stream) {
     if (!x || !gamma || !beta || !out) return fail("null argument");
-    CUDA_OK(launch_layernorm(x, (size_t)M, D, gamma, beta, gelu, out, nullptr, nullptr, (cudaStream_t)stream));
+    CUDA_OK(launch_layernorm(x, (size_t)M, D, gamma, beta, gelu, out, no_planes(), (cudaStream_t)stream));
     return 0;
 }
 
@@ -1655,7 +1719,7 @@ extern "C" int s3b_attention_f32(const float* q, const float* k, const float* v,
     TMAP_OK(encode_tmap_bf16_3d(&ap.vt_hi, vts.h(), T, 64, BH, Tp, (uint64_t)64 * Tp, 64, 64));
     TMAP_OK(encode_tmap_bf16_3d(&ap.vt_lo, vts.l(), T, 64, BH, Tp, (uint64_t)64 * Tp, 64, 64));
     ap.B = B, ap.H = H, ap.T = T, ap.D = D, ap.kv_len = kv.as<int>();
-    ap.ctx_hi = ctx.h(), ap.ctx_lo = ctx.l();
+    ap.ctx = ctx.planes(0);
     DevBuf trace;
     const char* tb = getenv("S3B_ATTN_TRACE_BLOCK");  // debug: dump a clock64 timeline of one CTA to stderr
     if (tb != nullptr) {

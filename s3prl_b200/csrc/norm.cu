@@ -13,8 +13,7 @@ template <int V4>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, size_t M,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, int gelu, float* out_f32,
-                                                        __nv_bfloat16* __restrict__ out_hi,
-                                                        __nv_bfloat16* __restrict__ out_lo) {
+                                                        const OutPlanes op) {
     constexpr int D = V4 * 128;
     const int lane = threadIdx.x & 31;
     const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -50,26 +49,20 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
         y.w = (v[i].w - mean) * rstd * g.w + b.w;
         if (gelu) y.x = gelu_erf(y.x), y.y = gelu_erf(y.y), y.z = gelu_erf(y.z), y.w = gelu_erf(y.w);
         if (out_f32 != nullptr) reinterpret_cast<float4*>(out_f32 + row * D)[c4] = y;
-        if (out_hi != nullptr) {
-            uint32_t h0, l0, h1, l1;
-            split_pack2(y.x, y.y, h0, l0);
-            split_pack2(y.z, y.w, h1, l1);
-            reinterpret_cast<uint2*>(out_hi + row * D)[c4] = make_uint2(h0, h1);
-            reinterpret_cast<uint2*>(out_lo + row * D)[c4] = make_uint2(l0, l1);
-        }
+        if (op.hi != nullptr) store_planes4(op, y, row * D + 4 * (size_t)c4);
     }
 }
 
 cudaError_t launch_layernorm(const float* x, size_t M, int D, const float* gamma, const float* beta, int gelu,
-                             float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t s) {
+                             float* out_f32, const OutPlanes& op, cudaStream_t s) {
     if (M == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((M + 7) / 8);
     cudaError_t e = cudaSuccess;
     switch (D) {
-        case 512: e = launch_pdl(layernorm_kernel<4>, dim3(blocks), dim3(256), 0, s, x, M, gamma, beta, gelu, out_f32, out_hi, out_lo); break;
-        case 768: e = launch_pdl(layernorm_kernel<6>, dim3(blocks), dim3(256), 0, s, x, M, gamma, beta, gelu, out_f32, out_hi, out_lo); break;
-        case 1024: e = launch_pdl(layernorm_kernel<8>, dim3(blocks), dim3(256), 0, s, x, M, gamma, beta, gelu, out_f32, out_hi, out_lo); break;
-        case 1280: e = launch_pdl(layernorm_kernel<10>, dim3(blocks), dim3(256), 0, s, x, M, gamma, beta, gelu, out_f32, out_hi, out_lo); break;
+        case 512: e = launch_pdl(layernorm_kernel<4>, dim3(blocks), dim3(256), 0, s, x, M, gamma, beta, gelu, out_f32, op); break;
+        case 768: e = launch_pdl(layernorm_kernel<6>, dim3(blocks), dim3(256), 0, s, x, M, gamma, beta, gelu, out_f32, op); break;
+        case 1024: e = launch_pdl(layernorm_kernel<8>, dim3(blocks), dim3(256), 0, s, x, M, gamma, beta, gelu, out_f32, op); break;
+        case 1280: e = launch_pdl(layernorm_kernel<10>, dim3(blocks), dim3(256), 0, s, x, M, gamma, beta, gelu, out_f32, op); break;
         default: return cudaErrorInvalidValue;
     }
     return e;
@@ -88,9 +81,7 @@ __global__ void __launch_bounds__(256) posconv_combine_kernel(const float* __res
                                                               const float* __restrict__ bias, int B, int T, int cpg,
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, int do_ln,
-                                                              float* __restrict__ out_f32,
-                                                              __nv_bfloat16* __restrict__ out_hi,
-                                                              __nv_bfloat16* __restrict__ out_lo) {
+                                                              float* __restrict__ out_f32, const OutPlanes op) {
     constexpr int D = V4 * 128;
     const int lane = threadIdx.x & 31;
     const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -144,26 +135,20 @@ __global__ void __launch_bounds__(256) posconv_combine_kernel(const float* __res
             y.w = (y.w - mean) * rstd * g.w + be.w;
         }
         if (out_f32 != nullptr) reinterpret_cast<float4*>(out_f32 + row * D)[c4] = y;
-        if (out_hi != nullptr) {
-            uint32_t h0, l0, h1, l1;
-            split_pack2(y.x, y.y, h0, l0);
-            split_pack2(y.z, y.w, h1, l1);
-            reinterpret_cast<uint2*>(out_hi + row * D)[c4] = make_uint2(h0, h1);
-            reinterpret_cast<uint2*>(out_lo + row * D)[c4] = make_uint2(l0, l1);
-        }
+        if (op.hi != nullptr) store_planes4(op, y, row * D + 4 * (size_t)c4);
     }
 }
 
 cudaError_t launch_posconv_combine(const float* z, const float* x, const float* bias, int B, int T, int D, int cpg,
                                    const float* gamma, const float* beta, int do_ln, float* out_f32,
-                                   __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t s) {
+                                   const OutPlanes& op, cudaStream_t s) {
     const size_t M = (size_t)B * T;
     if (M == 0) return cudaSuccess;
     if (cpg % 4 != 0) return cudaErrorInvalidValue;
     const unsigned blocks = (unsigned)((M + 7) / 8);
 #define S3B_PC(V)                                                                                                   \
     return launch_pdl(posconv_combine_kernel<V>, dim3(blocks), dim3(256), 0, s, z, x, bias, B, T, cpg, gamma, beta, \
-                      do_ln, out_f32, out_hi, out_lo)
+                      do_ln, out_f32, op)
     switch (D) {
         case 512: S3B_PC(4);
         case 768: S3B_PC(6);

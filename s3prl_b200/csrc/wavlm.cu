@@ -56,8 +56,7 @@ cudaError_t launch_wavlm_rel_table(const float* emb, int num_buckets, int max_di
 // groups of four before the sigmoids (modules.py:541-546: view(..., 2, 4).sum(-1)), so only the two summed weight
 // rows (and summed biases) are needed: 2 x 64 FMAs per thread instead of 8 x 64 (same value up to fp32 summation
 // order). The two combined rows are built in shared memory by every block.
-__global__ void __launch_bounds__(256) wavlm_gate_kernel(const __nv_bfloat16* __restrict__ x_hi,
-                                                         const __nv_bfloat16* __restrict__ x_lo, size_t M, int T,
+__global__ void __launch_bounds__(256) wavlm_gate_kernel(const OutPlanes xp, size_t M, int T,
                                                          int H, int D, const float* __restrict__ gw,
                                                          const float* __restrict__ gb, const float* __restrict__ ga,
                                                          float* __restrict__ gate) {
@@ -86,15 +85,12 @@ __global__ void __launch_bounds__(256) wavlm_gate_kernel(const __nv_bfloat16* __
     if (gw != nullptr) {  // kernel-uniform
         float sa = 0.f, sb = 0.f;
         if (ok) {
-            const size_t off = m * (size_t)D + (size_t)h * 64;
-            const uint4 vh = reinterpret_cast<const uint4*>(x_hi + off)[c];
-            const uint4 vl = reinterpret_cast<const uint4*>(x_lo + off)[c];
-            const uint32_t wh[4] = {vh.x, vh.y, vh.z, vh.w}, wl[4] = {vl.x, vl.y, vl.z, vl.w};
+            const size_t off = m * (size_t)D + (size_t)h * 64 + 8 * (size_t)c;
             float xv[8];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                xv[2 * e] = __uint_as_float(wh[e] << 16) + __uint_as_float(wl[e] << 16);
-                xv[2 * e + 1] = __uint_as_float(wh[e] & 0xffff0000u) + __uint_as_float(wl[e] & 0xffff0000u);
+                const float2 v2 = load_planes2(xp, off + 2 * e);
+                xv[2 * e] = v2.x, xv[2 * e + 1] = v2.y;
             }
             const float4* w0 = reinterpret_cast<const float4*>(sw);
             const float4* w1 = reinterpret_cast<const float4*>(sw + 64);
@@ -117,13 +113,12 @@ __global__ void __launch_bounds__(256) wavlm_gate_kernel(const __nv_bfloat16* __
     if (ok && c == 0) gate[((size_t)b * H + h) * T + t] = g1;
 }
 
-cudaError_t launch_wavlm_gate(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, size_t M, int B, int T, int H,
-                              int D, const float* grep_w, const float* grep_b, const float* grep_a, float* gate,
-                              cudaStream_t s) {
+cudaError_t launch_wavlm_gate(const OutPlanes& xp, size_t M, int B, int T, int H, int D, const float* grep_w,
+                              const float* grep_b, const float* grep_a, float* gate, cudaStream_t s) {
     (void)B;
     const size_t n = M * (size_t)H * 8;  // eight lanes per (token, head)
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    wavlm_gate_kernel<<<blocks, 256, 0, s>>>(x_hi, x_lo, M, T, H, D, grep_w, grep_b, grep_a, gate);
+    wavlm_gate_kernel<<<blocks, 256, 0, s>>>(xp, M, T, H, D, grep_w, grep_b, grep_a, gate);
     return cudaGetLastError();
 }
 

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "common.cuh"
+
 namespace s3b {
 
 // Host: bucket index of relative position `rel` = key - query (bit-exact restatement of
@@ -16,9 +18,8 @@ cudaError_t launch_wavlm_rel_table(const float* emb /*[num_buckets][H] device*/,
 
 // gate[b][h][t] = ga*(gb*grep_a[h]-1)+2, (ga,gb) = sigmoid(sum4(grep_linear(x[b,t,h*64:(h+1)*64])))
 // (modules.py:534-551). grep_w == nullptr (gru_rel_pos off) -> gate = 1.
-cudaError_t launch_wavlm_gate(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, size_t M, int B, int T, int H,
-                              int D, const float* grep_w, const float* grep_b, const float* grep_a, float* gate,
-                              cudaStream_t s);
+cudaError_t launch_wavlm_gate(const OutPlanes& xp, size_t M, int B, int T, int H, int D, const float* grep_w,
+                              const float* grep_b, const float* grep_a, float* gate, cudaStream_t s);
 
 // test helpers: fp32 [B][T][H*64] q/k/v -> the attention kernel's operand layout; hi+lo -> fp32
 cudaError_t launch_qkv_scatter(const float* q, const float* k, const float* v, int B, int T, int Tp, int H,

@@ -257,3 +257,33 @@ def test_fused_layernorm_is_bit_identical(s3b_lib, name):
         finally:
             expert.lanes = 0
         assert torch.equal(got, ref), (name, lanes)
+
+
+@pytest.mark.parametrize("name", ["hubert_base", "wav2vec2_large_ll60k", "wavlm_base_plus"])
+def test_operand_schemes_agree(s3b_lib, name):
+    """The two tensor-core operand schemes of the conv / linear GEMMs — bf16 hi/lo with 3 MMAs per product, and fp16 with
+    two e4m3 correction products (2 MMA slots, S3B_GEMM_SCHEME=f16q8) — both reproduce the oracle within the parity
+    tolerance and agree with each other to well inside it."""
+    import upstream_oracle as O
+    from s3prl_b200.upstream.configs import ARCHS
+    from s3prl_b200.upstream.expert import UpstreamExpert
+    from s3prl_b200.upstream.weights import fabricate_state_dict
+
+    cfg = ARCHS[name]
+    wavs = _wavs([24000, 17003], seed=77)
+    with torch.no_grad():
+        ref, _ = O.upstream_forward(wavs, fabricate_state_dict(cfg, 0), cfg)
+    outs = {}
+    _EXPERTS.clear()
+    for scheme in ("bf16x3", "f16q8"):
+        os.environ["S3B_GEMM_SCHEME"] = scheme
+        try:
+            e = UpstreamExpert(name=name, seed=0).to("cuda")
+            outs[scheme] = [h.cpu() for h in e([w.cuda() for w in wavs])["hidden_states"]]
+            del e
+        finally:
+            os.environ.pop("S3B_GEMM_SCHEME", None)
+        worst = max(_compare(h, r, f"{name} {scheme} layer {l}") for l, (h, r) in enumerate(zip(outs[scheme], ref)))
+        print(f"{name} {scheme}: worst per-layer relative error vs oracle = {worst:.3e}")
+    for a, b in zip(outs["bf16x3"], outs["f16q8"]):
+        assert ((a.double() - b.double()).norm() / b.double().norm()).item() < 1e-4
