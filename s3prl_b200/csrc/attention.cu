@@ -333,10 +333,11 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
             tmem_ld_wait();
             if (row_ok) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 y = make_float4(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv,
-                                                 __uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
-                    store_planes4(p.ctx, y, off + c + i);
+                for (int i = 0; i < 32; i += 8) {
+                    float y[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) y[e] = __uint_as_float(v[i + e]) * inv;
+                    store_planes8(p.ctx, y, off + c + i);
                 }
             }
         }

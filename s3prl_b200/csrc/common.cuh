@@ -142,6 +142,26 @@ __device__ __forceinline__ void store_planes4(const OutPlanes& o, const float4& 
         *reinterpret_cast<uint2*>(o.lo + elem) = make_uint2(l0, l1);
     }
 }
+// eight consecutive elements (elem % 8 == 0): 16-byte stores on the 2-byte planes
+__device__ __forceinline__ void store_planes8(const OutPlanes& o, const float (&y)[8], size_t elem) {
+    if (o.fmt != 0) {
+        uint32_t h[4];
+        uint16_t a[4], b[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_q8_pack2(y[2 * e], y[2 * e + 1], h[e], a[e], b[e]);
+        *reinterpret_cast<uint4*>(o.hi + elem) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint2*>(o.h8 + elem) =
+            make_uint2((uint32_t)a[0] | ((uint32_t)a[1] << 16), (uint32_t)a[2] | ((uint32_t)a[3] << 16));
+        *reinterpret_cast<uint2*>(o.l8 + elem) =
+            make_uint2((uint32_t)b[0] | ((uint32_t)b[1] << 16), (uint32_t)b[2] | ((uint32_t)b[3] << 16));
+    } else {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_pack2(y[2 * e], y[2 * e + 1], h[e], l[e]);
+        *reinterpret_cast<uint4*>(o.hi + elem) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(o.lo + elem) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
 // two consecutive elements (elem % 2 == 0)
 __device__ __forceinline__ void store_planes2(const OutPlanes& o, float y0, float y1, size_t elem) {
     if (o.fmt != 0) {

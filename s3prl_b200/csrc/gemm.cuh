@@ -20,6 +20,8 @@ struct GemmParams {
     //   a_hi / b_hi are the fp16 planes (box {64, rows}), a_h8 / a_l8 / b_h8 / b_l8 the e4m3 planes (box {128, rows});
     //   k-blocks are 128 elements wide: block_k == 128, K % 128 == 0; a_lo / b_lo are unused.
     int scheme;
+    int q8_debug;  // s3b_gemm_bench only (timing experiments, wrong numerics): 1 = corrections issued as kind::f16,
+                   // 2 = no scale-input-d, 3 = correction MMAs skipped, 4 = main MMAs skipped
     CUtensorMap a_h8, a_l8, b_h8, b_l8;
 
     // ---- tiling -------------------------------------------------------------------------------

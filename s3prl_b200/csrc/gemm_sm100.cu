@@ -710,11 +710,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
                                     const uint64_t ko = (uint64_t)(k * 2);
                                     const uint64_t da = (t == 0 ? da0 : da1) + ko, db = (t == 0 ? db0 : db1) + ko;
                                     if (pass == 0) {
-                                        umma_q8_2cta(d_tmem, da, db, idesc, (kb | t | k) != 0 ? 1u : 0u);
-                                    } else if ((kb | t | k) == 0) {
+                                        if (p.q8_debug == 1) umma_bf16_2cta(d_tmem, da, db, idesc, (kb | t | k) != 0 ? 1u : 0u);
+                                        else if (p.q8_debug != 3) umma_q8_2cta(d_tmem, da, db, idesc, (kb | t | k) != 0 ? 1u : 0u);
+                                    } else if ((kb | t | k) == 0 && p.q8_debug != 2 && p.q8_debug != 3) {
                                         umma_f16_2cta_scaled(d_tmem, da, db, idesc);  // D = A*B + D * 2^-kQ8Scale
-                                    } else {
-                                        umma_bf16_2cta(d_tmem, da, db, idesc, 1u);  // kind::f16, formats from idesc
+                                    } else if (p.q8_debug != 4 || (kb | t | k) == 0) {
+                                        umma_bf16_2cta(d_tmem, da, db, idesc, (p.q8_debug == 3 && (kb | t | k) == 0) ? 0u : 1u);
                                     }
                                 }
                             }
@@ -786,6 +787,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
                 if (leader) mbar_arrive(&tmem_empty[acc]);
                 else mbar_arrive_remote(&tmem_empty[acc], 0);
             }
+#ifdef S3B_ENABLE_FUSED_LN
+            // Compiled out by default: the call below costs the epilogue loop ~50 registers of caller-saved state
+            // (ptxas then keeps the residual prefetch array in local memory), which slowed EVERY GEMM by ~6 %, more than
+            // the fusion can win back (measured, profiles/README.md r2d / r2f). The code is kept for the experiment.
             if (p.ln_gamma != nullptr) {
                 // ---- fused LayerNorm: the last CTA to finish its n-tile of these 128 rows normalises them ------------
                 // (all 8 epilogue warps of this CTA take part; named barrier 1 = the epilogue warps only)
@@ -805,6 +810,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
                     ln_tile_rows(&p, batch, row0, warp - 4, lane);
                 }
             }
+#endif
             if (etr) p.trace[ntile_done == 0 ? 6 : 8] = (unsigned long long)clock64();
             if (++acc == 2) acc = 0, acc_phase ^= 1u;
         }
@@ -838,6 +844,9 @@ static cudaError_t launch_pair(const GemmParams& p, int sm_count, cudaStream_t s
         return cudaErrorInvalidValue;
     if (p.out_fmt != 0 && (p.qkv_mode || (p.out_hi != nullptr && (p.out_h8 == nullptr || p.out_l8 == nullptr))))
         return cudaErrorInvalidValue;
+#ifndef S3B_ENABLE_FUSED_LN
+    if (p.ln_gamma != nullptr) return cudaErrorNotSupported;
+#endif
     if (p.ln_gamma != nullptr &&
         (p.out_f32 == nullptr || p.ln_counter == nullptr || p.qkv_mode || p.n_tiles * p.umma_n != p.ldo ||
          (p.ldo != 512 && p.ldo != 768 && p.ldo != 1024 && p.ldo != 1280)))

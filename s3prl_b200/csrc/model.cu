@@ -772,6 +772,9 @@ static inline void prof_end(s3b_model* m, cudaStream_t st, int cat, int nkernels
 // S3B_FUSE_LN: 0 = never, 1 = wherever possible, unset = only where the tile's MMAs (K >= 2048: fc2) leave the epilogue
 // warps the slack to do it (measured, profiles/r2d: fusing behind the K = 768 out_proj made its tiles epilogue-bound)
 static int fuse_ln_mode() {
+#ifndef S3B_ENABLE_FUSED_LN
+    return 0;  // not compiled in (see gemm_sm100.cu): every LayerNorm is its own launch
+#endif
     const char* e = getenv("S3B_FUSE_LN");  // read per call: tests toggle it (the plan cache is keyed on it)
     if (!pairs_enabled()) return 0;
     if (e == nullptr) return 2;
@@ -1661,6 +1664,7 @@ extern "C" int s3b_gemm_bench(int64_t M, int32_t N, int32_t K, int32_t gelu, int
     if (K % 128 != 0 || N % 128 != 0 || !pairs_enabled()) scheme = 0;
     int r = linear_params(p, as, ws, M, N, K, gelu ? 2 : 0, scheme);
     g_force_pair_un = 0;
+    if (const char* dbg = getenv("S3B_Q8_DEBUG")) p.q8_debug = atoi(dbg);
     if (r == 0) {
         Epi e;
         e.bias = bias.as<float>();
