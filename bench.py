@@ -455,13 +455,16 @@ def run_ours(args):
         # gathered features copied to pinned host memory. Wall clock, max over ranks.
         feat_host = torch.empty((GLOBAL_BATCH, T, D), dtype=torch.float32).pin_memory()
 
+        e2e_gathered = torch.empty((GLOBAL_BATCH, T, D), dtype=torch.float32, device=device) if world > 1 else None
+
         def e2e_step():
             out_host, hs_dev = expert.forward_host(wavs_host, keep_device=True)
-            if gatherer is not None:
-                feat = gatherer.weighted_sum_gather([hs_dev[i] for i in range(NLp1)], fw)
-                gatherer.finish()
-            else:
-                feat = weighted_sum([hs_dev[i] for i in range(NLp1)], fw)
+            feat = weighted_sum([hs_dev[i] for i in range(NLp1)], fw)
+            if world > 1:
+                # the end-to-end step is bound by the host<->device copies and synchronises every step anyway: plain
+                # NCCL here (measured at N = 8: 3.74 M frames/s vs 2.42 M with the flag-polling push path, r2j)
+                dist.all_gather_into_tensor(e2e_gathered, feat)
+                feat = e2e_gathered
             feat_host.copy_(feat, non_blocking=True)
             torch.cuda.synchronize()
             return out_host

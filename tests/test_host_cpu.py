@@ -340,7 +340,8 @@ def test_synthetic_batches_follow_collect_audio_batch_rules():
             assert max(lens) <= 24 * 16000
         if len(wavs) == 32:
             seen_full = True
-            assert max(lens) <= 300000 and min(lens) >= 2 * 16000
+            # (the rule looks at the bucket's FIRST utterance, which need not be its longest)
+            assert max(lens) <= 24 * 16000 and min(lens) >= 2 * 16000
         assert len(wavs) in (16, 32)
         if i > 200:
             break
