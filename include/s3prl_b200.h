@@ -22,7 +22,7 @@ typedef struct s3b_model s3b_model;
  * Wav2Vec2Config (s3prl/upstream/wav2vec2/wav2vec2_model.py:2103-2350) and
  * WavLMConfig (s3prl/upstream/wavlm/WavLM.py:162-245) that the extraction forward reads. */
 typedef struct s3b_config {
-    int32_t family;               /* 0 = hubert, 1 = wav2vec2, 2 = wavlm (selects frame-mask rule, T2 handling) */
+    int32_t family;               /* 0 = hubert, 1 = wav2vec2, 2 = wavlm, 3 = distiller (selects the frame-mask rule) */
     int32_t extractor_layer_norm; /* 0: extractor_mode "default" (GroupNorm after conv 0); 1: "layer_norm" */
     int32_t conv_bias;            /* conv_bias */
     int32_t layer_norm_first;     /* pre-LN transformer (large_ll60k, wavlm_large) */
@@ -37,7 +37,10 @@ typedef struct s3b_config {
     int32_t num_buckets;          /* WavLM num_buckets (320) */
     int32_t max_distance;         /* WavLM max_distance (800) */
     int32_t gru_rel_pos;          /* WavLM gru_rel_pos */
-    int32_t reserved[8];
+    /* Distiller / DistilHuBERT (s3prl/upstream/distiller/model.py:81-269): */
+    int32_t no_feature_layer_norm; /* 1: post_extract_proj takes the conv features directly (no LayerNorm(512)) */
+    int32_t pred_heads;            /* n_tasks prediction heads Linear -> GELU -> SplitLinear on the encoder output (0: none) */
+    int32_t reserved[6];
 } s3b_config;
 
 /* Library / error ------------------------------------------------------------------------------ */
@@ -74,8 +77,11 @@ int s3b_valid_frames(const s3b_model* m, const int64_t* lens, int32_t batch, int
  *  lens        : host array of `batch` lengths (samples)
  *  max_len     : padded batch length Lmax (>= max(lens); equal to it for single-GPU use; the global max of
  *                the un-sharded batch when the batch is sharded across ranks)
- *  hidden_out  : DEVICE buffer [num_layers+1][batch][T][embed_dim] fp32, T = s3b_num_frames(max_len)
+ *  hidden_out  : DEVICE buffer [s3b_num_outputs(m)][batch][T][embed_dim] fp32, T = s3b_num_frames(max_len):
+ *                num_layers+1 hidden states (input of every layer + encoder output); for a distiller model
+ *                (distiller/expert.py:44-63) feat_final, the num_layers layer outputs, then the pred_heads predictions
  *  stream      : cudaStream_t the work is enqueued on (asynchronous with respect to the host) */
+int32_t s3b_num_outputs(const s3b_model* m);
 int s3b_forward(s3b_model* m, const float* const* wavs, const int64_t* lens, int32_t batch, int64_t max_len,
                 float* hidden_out, void* stream);
 /* Same, end-to-end from HOST buffers: waveforms are host pointers, hidden_out is a host buffer; the

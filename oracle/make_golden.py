@@ -42,6 +42,7 @@ CASES = {
     "hubert_large_ll60k": ([[12000, 7001]], 13),
     "unispeech_sat_base_plus": ([[16000, 12345, 800], [8000, 8000]], 7),
     "unispeech_sat_large": ([[12000, 7001]], 13),
+    "distilhubert_base": ([[16000, 12345, 3200], [8000, 8000]], 7),
 }
 
 

@@ -51,7 +51,18 @@ def reference_expert(name: str, sd):
     tmp = tempfile.NamedTemporaryFile(suffix=".pt", delete=False)
     tmp.close()
     try:
-        if cfg.family == "hubert":
+        if cfg.family == "distiller":
+            from s3prl.upstream.distiller.expert import UpstreamExpert
+            from s3prl.upstream.distiller.model import DistillerConfig, DistillerModel
+
+            from s3prl_b200.upstream.convert import distiller_config
+
+            dcfg = distiller_config(cfg)
+            skeleton = DistillerModel(DistillerConfig(dcfg))
+            full = skeleton.state_dict()
+            full.update(sd)
+            torch.save({"Config": {"distiller": dcfg}, "Distiller": full}, tmp.name)
+        elif cfg.family == "hubert":
             from s3prl.upstream.hubert.expert import UpstreamExpert
             from s3prl.upstream.hubert.hubert_model import HubertConfig, HubertModel, HubertPretrainingConfig
             from s3prl.upstream.utils import merge_with_parent

@@ -66,6 +66,8 @@ def frame_padding_mask_conv_length(sample_mask: torch.Tensor, T: int) -> Optiona
 def valid_frames(family: str, lens: Sequence[int], max_len: int) -> List[int]:
     """Un-padded frame count per utterance implied by the family's frame mask rule."""
     T = conv_output_length(max_len)
+    if family == "distiller":
+        return distiller_valid_frames(lens, T)
     sm = sample_padding_mask(lens, max_len)
     fm = frame_padding_mask_conv_length(sm, T) if family == "wav2vec2" else frame_padding_mask_chunk_all(sm, T)
     if fm is None:
@@ -203,6 +205,8 @@ def upstream_forward(
     pad-to-multiple-of-2 column (wav2vec2_model.py:3073-3082) is a masked key whose query row is discarded by
     hook_postprocess (hubert/expert.py:45-51): it cannot influence the returned frames and is omitted.
     """
+    if getattr(cfg, "family", None) == "distiller":
+        return distiller_forward(wavs, sd, cfg, max_len)
     sd = {k: v.float() for k, v in sd.items() if torch.is_tensor(v) and v.is_floating_point()}
     wavs = [w.float() for w in wavs]
     lens = [len(w) for w in wavs]
@@ -253,6 +257,66 @@ def upstream_forward(
         h = ln(h, "encoder.layer_norm")  # TransformerEncoder.forward, wav2vec2_model.py:3049-3050
     hidden.append(h)
     return hidden, pad
+
+
+def distiller_valid_frames(lens: Sequence[int], T: int) -> List[int]:
+    """DistillerModel.cal_pad_mask (s3prl/upstream/distiller/model.py:272-286): the conv length formula with
+    truncating division on every utterance (padded batch or not); frames >= that length are padding."""
+    out = []
+    for n in lens:
+        for _d, k, s_ in CONV_LAYERS:
+            n = int((n - k) / s_) + 1  # torch.div(..., rounding_mode="trunc")
+        out.append(max(0, min(n, T)) if n >= 0 else max(0, T + n))  # new_pad_mask[idx, n:] = 0 (Python slice semantics)
+    return out
+
+
+def distiller_forward(wavs: Sequence[torch.Tensor], sd: Dict[str, torch.Tensor], cfg, max_len: Optional[int] = None):
+    """hidden_states of the Distiller expert (s3prl/upstream/distiller/expert.py:44-63):
+    [feat_final] + layer outputs + prediction heads, and the frame padding mask.
+    Follows DistillerModel.forward (distiller/model.py:187-269: no LayerNorm in front of post_extract_proj; the
+    encoder zeroes the padded frames of feat_final IN PLACE, so the returned feat_final carries the zeros), the
+    TransformerEncoder of distiller/module.py:292-334 (layer outputs are collected) and the output layer
+    Linear -> GELU -> SplitLinear (model.py:150-160, module.py:55-90)."""
+    sd = {k: v.float() for k, v in sd.items() if torch.is_tensor(v) and v.is_floating_point()}
+    wavs = [w.float() for w in wavs]
+    lens = [len(w) for w in wavs]
+    x = pad_waveforms(wavs, False, max_len)
+    feats = conv_feature_extractor(x, sd, cfg.extractor_mode, False).transpose(1, 2)  # [B, T, 512]
+    B, T, _ = feats.shape
+    valid = distiller_valid_frames(lens, T)
+    pad = torch.arange(T).unsqueeze(0) >= torch.tensor(valid).unsqueeze(1)
+    feat_final = F.linear(feats, sd["post_extract_proj.weight"], sd["post_extract_proj.bias"])
+    feat_final = feat_final.masked_fill(pad.unsqueeze(-1), 0.0)
+    h = feat_final + positional_conv(feat_final, sd, cfg.conv_pos_groups)
+    if not cfg.layer_norm_first:
+        h = F.layer_norm(h, (h.size(-1),), sd["encoder.layer_norm.weight"], sd["encoder.layer_norm.bias"], 1e-5)
+
+    def ln(t, name):
+        return F.layer_norm(t, (t.size(-1),), sd[f"{name}.weight"], sd[f"{name}.bias"], 1e-5)
+
+    heads = cfg.encoder_attention_heads
+    layer_out = []
+    for l in range(cfg.encoder_layers):
+        p = f"encoder.layers.{l}"
+        if cfg.layer_norm_first:
+            a = self_attention(ln(h, f"{p}.self_attn_layer_norm"), sd, f"{p}.self_attn", heads, pad)
+            h = h + a
+            f = ln(h, f"{p}.final_layer_norm")
+            h = h + F.linear(F.gelu(F.linear(f, sd[f"{p}.fc1.weight"], sd[f"{p}.fc1.bias"])), sd[f"{p}.fc2.weight"], sd[f"{p}.fc2.bias"])
+        else:
+            a = self_attention(h, sd, f"{p}.self_attn", heads, pad)
+            h = ln(h + a, f"{p}.self_attn_layer_norm")
+            f = F.linear(F.gelu(F.linear(h, sd[f"{p}.fc1.weight"], sd[f"{p}.fc1.bias"])), sd[f"{p}.fc2.weight"], sd[f"{p}.fc2.bias"])
+            h = ln(h + f, f"{p}.final_layer_norm")
+        layer_out.append(h)
+    hidden = ln(h, "encoder.layer_norm") if cfg.layer_norm_first else h
+    N = cfg.pred_heads
+    z = F.gelu(F.linear(hidden, sd["output_layer.0.weight"], sd["output_layer.0.bias"]))  # [B, T, N*D]
+    D = hidden.size(-1)
+    z = z.reshape(B, T, N, 1, D)
+    pred = torch.einsum("...klm,kmn->...kln", z, sd["output_layer.2.weight"]).squeeze(3) + sd["output_layer.2.bias"]
+    preds = [pred[:, :, i, :] for i in range(N)]
+    return [feat_final] + layer_out + preds, pad
 
 
 def weighted_sum(hidden: Sequence[torch.Tensor], weights: torch.Tensor) -> torch.Tensor:

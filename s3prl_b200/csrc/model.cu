@@ -168,7 +168,7 @@ struct Workspace {
     size_t book_host_bytes = 0;
     size_t book_valid = 0;  // bytes of the mirror that hold the last call's block
     cudaEvent_t book_copied = nullptr;  // the previous call's H2D copy has been consumed: the mirror may be rewritten
-    DevBuf wav_stats, wav_pad, c0_part, c0_ss, conv_f32, tmp_f32, x_f32, x1_f32, gate, pos_z, ln_counters;
+    DevBuf wav_stats, wav_pad, c0_part, c0_ss, conv_f32, tmp_f32, x_f32, x1_f32, gate, pos_z, ln_counters, hs0;
     SplitBuf act[kNumConv], ln512_s, x_s, xs_s, q_s, k_s, vt_s, ctx_s, x1_s, h_s;
     cudaStream_t stream = nullptr;  // lane stream (lane 1; lane 0 runs on the caller's stream)
     cudaEvent_t done = nullptr;
@@ -194,6 +194,9 @@ struct s3b_model {
     DevBuf conv_b[kNumConv], conv_ln_g[kNumConv], conv_ln_b[kNumConv];
     DevBuf ln512_g, ln512_b, proj_b, pos_b, enc_ln_g, enc_ln_b;
     SplitBuf proj_w, pos_w, pos_w4;  // pos_w4: four-taps-per-k-block layout (posconv4_params)
+    SplitBuf pred1_w;                   // Distiller output_layer.0.weight [N*D][D]
+    std::vector<SplitBuf> pred2_w;      // Distiller output_layer.2.weight, per task, transposed to [D out][D in]
+    DevBuf pred1_b, pred2_b;            // biases [N*D]
     DevBuf rel_table_src;  // WavLM relative_attention_bias.weight [num_buckets][H]
     DevBuf rel_table;      // [H][2*rel_table_T - 1] gathered table (x log2 e), built at finalize for rel_table_T frames
     int rel_table_T = 0;
@@ -301,6 +304,13 @@ extern "C" int s3b_model_create(const s3b_config* cfg, s3b_model** out) {
     if (cpg % 16 != 0 || cpg > 64) return fail("channels per pos_conv group must be a multiple of 16, <= 64");
     if (cfg->pos_conv_kernel % 2 != 0) return fail("pos_conv_kernel must be even");
     if (cfg->num_layers < 1 || cfg->num_layers > 63) return fail("num_layers out of range");
+    if (cfg->family < 0 || cfg->family > 3) return fail("family must be 0 (hubert), 1 (wav2vec2), 2 (wavlm) or 3 (distiller)");
+    if (cfg->pred_heads < 0 || cfg->pred_heads > 12 || cfg->pred_heads * cfg->embed_dim > cfg->ffn_dim)
+        return fail("pred_heads out of range (needs pred_heads * embed_dim <= ffn_dim)");
+    if (cfg->no_feature_layer_norm && cfg->extractor_layer_norm)
+        return fail("no_feature_layer_norm with extractor_mode layer_norm is not supported");
+    if ((cfg->family == 3) != (cfg->no_feature_layer_norm != 0))
+        return fail("the distiller family (3) and no_feature_layer_norm go together");
     s3b_model* m = new s3b_model();
     m->cfg = *cfg;
     m->scheme = default_scheme();
@@ -328,8 +338,10 @@ extern "C" void s3b_model_destroy(s3b_model* m) {
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < kNumConv; ++i)
         m->conv_w[i].release(), m->conv_b[i].release(), m->conv_ln_g[i].release(), m->conv_ln_b[i].release();
-    SplitBuf* sb[] = {&m->proj_w, &m->pos_w, &m->pos_w4};
+    SplitBuf* sb[] = {&m->proj_w, &m->pos_w, &m->pos_w4, &m->pred1_w};
     for (SplitBuf* b : sb) b->release();
+    for (SplitBuf& b : m->pred2_w) b.release();
+    m->pred1_b.release(), m->pred2_b.release();
     for (LayerW& l : m->layers) {
         l.qkv.release(), l.out.release(), l.fc1.release(), l.fc2.release();
         DevBuf* lb[] = {&l.qkv_b, &l.out_b, &l.fc1_b, &l.fc2_b, &l.ln1_g, &l.ln1_b, &l.ln2_g, &l.ln2_b,
@@ -404,8 +416,10 @@ extern "C" int s3b_model_finalize(s3b_model* m) {
         }
     }
     // ---- LayerNorm(512) + post_extract_proj ----------------------------------------------------------
-    S3B_OK(upload_vec(m, "layer_norm.weight", C, m->ln512_g));
-    S3B_OK(upload_vec(m, "layer_norm.bias", C, m->ln512_b));
+    if (!c.no_feature_layer_norm) {
+        S3B_OK(upload_vec(m, "layer_norm.weight", C, m->ln512_g));
+        S3B_OK(upload_vec(m, "layer_norm.bias", C, m->ln512_b));
+    }
     S3B_OK(need(m, "post_extract_proj.weight", {D, C}, &t));
     S3B_OK(upload_split(m->proj_w, t->data.data(), t->numel(), m->scheme));
     S3B_OK(upload_vec(m, "post_extract_proj.bias", D, m->proj_b));
@@ -492,6 +506,25 @@ extern "C" int s3b_model_finalize(s3b_model* m) {
             S3B_OK(upload_f32(L.grep_a, t->data.data(), t->numel()));
         }
     }
+    if (c.pred_heads > 0) {
+        // output_layer = Linear(D, N*D) -> GELU -> SplitLinear(D, N, D) (distiller/model.py:150-160); SplitLinear keeps
+        // its weight as [task][in][out] (module.py:66-73): transposed per task to the [out][in] layout of the GEMM
+        const int N = c.pred_heads;
+        S3B_OK(need(m, "output_layer.0.weight", {(int64_t)N * D, D}, &t));
+        S3B_OK(upload_split(m->pred1_w, t->data.data(), t->numel(), m->scheme));
+        S3B_OK(upload_vec(m, "output_layer.0.bias", (int64_t)N * D, m->pred1_b));
+        S3B_OK(need(m, "output_layer.2.weight", {N, D, D}, &t));
+        m->pred2_w.resize(N);
+        std::vector<float> wt((size_t)D * D);
+        for (int k = 0; k < N; ++k) {
+            for (int i = 0; i < D; ++i)
+                for (int o = 0; o < D; ++o) wt[(size_t)o * D + i] = t->data[((size_t)k * D + i) * D + o];
+            S3B_OK(upload_split(m->pred2_w[k], wt.data(), wt.size(), m->scheme));
+        }
+        const HostTensor* tb;
+        S3B_OK(need(m, "output_layer.2.bias", {1, 1, N, D}, &tb));
+        S3B_OK(upload_f32(m->pred2_b, tb->data.data(), tb->numel()));
+    }
     if (c.relative_position) {
         S3B_OK(need(m, "encoder.layers.0.self_attn.relative_attention_bias.weight", {c.num_buckets, c.num_heads}, &t));
         S3B_OK(upload_f32(m->rel_table_src, t->data.data(), t->numel()));
@@ -508,6 +541,10 @@ extern "C" int s3b_model_finalize(s3b_model* m) {
 extern "C" int64_t s3b_num_frames(const s3b_model*, int64_t max_len) {
     const int64_t T = num_frames(max_len);
     return T > 0 ? T : -1;
+}
+
+extern "C" int32_t s3b_num_outputs(const s3b_model* m) {
+    return m ? m->cfg.num_layers + 1 + m->cfg.pred_heads : -1;
 }
 
 extern "C" int s3b_valid_frames(const s3b_model* m, const int64_t* lens, int32_t batch, int64_t max_len,
@@ -538,6 +575,13 @@ extern "C" int s3b_valid_frames(const s3b_model* m, const int64_t* lens, int32_t
                 if (idx < 0) idx += T;
                 v = idx + 1;
             }
+        } else if (m->cfg.family == 3) {
+            // Distiller: conv length formula with truncating division, always applied (distiller/model.py:272-286)
+            int64_t n = lens[b];
+            for (int i = 0; i < kNumConv; ++i) n = (n - kConvK[i]) / kConvS[i] + 1;  // C++ division truncates
+            if (n < 1) return fail("lens[%d]=%lld yields no valid frame: the reference's attention would see only padding",
+                                   b, (long long)lens[b]);
+            v = n;
         } else {
             // HuBERT / WavLM: frame t is padding iff all samples of chunk t are padding, chunk = Lmax // T
             const int64_t chunk = max_len / T;
@@ -641,9 +685,11 @@ static int pick_umma_n(int N) {
 // out[M][N] = A[M][K] * W[N][K]^T, flat token-major A (hi/lo planes), K % 64 == 0
 // epi_kind: 0 = fp32 output, 1 = bf16 hi/lo output (QKV scatter included), 2 = GELU + hi/lo (tile-width choice only)
 // scheme 1: A and W are f16q8 operands (SplitBuf fmt 1), K % 128 == 0.
+// lda / a_off: A is the [M][K] column slice starting at element a_off of rows that are lda elements apart (0 = dense).
 static int linear_params(GemmParams& p, const SplitBuf& A, const SplitBuf& W, int64_t M, int N, int K, int epi_kind = 0,
-                         int scheme = 0) {
+                         int scheme = 0, int64_t lda = 0, size_t a_off = 0) {
     memset(&p, 0, sizeof(p));
+    if (lda == 0) lda = K;
     if (K % 64 != 0 || N % 16 != 0)  // K % 64 keeps both k-block widths legal
         return fail("linear: K %% 64 or N %% 16 violated (N=%d K=%d)", N, K);
     int un = pick_umma_n(N);
@@ -652,9 +698,9 @@ static int linear_params(GemmParams& p, const SplitBuf& A, const SplitBuf& W, in
     const int pair = use_cta_pairs(un);
     if (scheme != 0) {
         if (!pair || K % 128 != 0) return fail("f16q8 GEMM needs CTA pairs and K %% 128 == 0 (N=%d K=%d)", N, K);
-        TMAP_OK(encode_tmap_bf16_3d(&p.a_hi, A.h(), K, M, 1, K, (uint64_t)M * K, 64, 128));
-        TMAP_OK(encode_tmap_u8_3d(&p.a_h8, A.h8(), K, M, 1, K, (uint64_t)M * K, 128, 128));
-        TMAP_OK(encode_tmap_u8_3d(&p.a_l8, A.l8(), K, M, 1, K, (uint64_t)M * K, 128, 128));
+        TMAP_OK(encode_tmap_bf16_3d(&p.a_hi, A.h() + a_off, K, M, 1, lda, (uint64_t)M * lda, 64, 128));
+        TMAP_OK(encode_tmap_u8_3d(&p.a_h8, A.h8() + a_off, K, M, 1, lda, (uint64_t)M * lda, 128, 128));
+        TMAP_OK(encode_tmap_u8_3d(&p.a_l8, A.l8() + a_off, K, M, 1, lda, (uint64_t)M * lda, 128, 128));
         TMAP_OK(encode_tmap_bf16_3d(&p.b_hi, W.h(), K, N, 1, K, (uint64_t)N * K, 64, un / 2));
         TMAP_OK(encode_tmap_u8_3d(&p.b_h8, W.h8(), K, N, 1, K, (uint64_t)N * K, 128, un / 2));
         TMAP_OK(encode_tmap_u8_3d(&p.b_l8, W.l8(), K, N, 1, K, (uint64_t)N * K, 128, un / 2));
@@ -662,8 +708,8 @@ static int linear_params(GemmParams& p, const SplitBuf& A, const SplitBuf& W, in
     } else {
         const int bk = pair ? 64 : gemm_block_k(un);
         const int bbox = pair ? un / 2 : un;  // CTA pairs: each CTA loads half of the tile's W rows
-        TMAP_OK(encode_tmap_bf16_3d(&p.a_hi, A.h(), K, M, 1, K, (uint64_t)M * K, bk, 128));
-        TMAP_OK(encode_tmap_bf16_3d(&p.a_lo, A.l(), K, M, 1, K, (uint64_t)M * K, bk, 128));
+        TMAP_OK(encode_tmap_bf16_3d(&p.a_hi, A.h() + a_off, K, M, 1, lda, (uint64_t)M * lda, bk, 128));
+        TMAP_OK(encode_tmap_bf16_3d(&p.a_lo, A.l() + a_off, K, M, 1, lda, (uint64_t)M * lda, bk, 128));
         TMAP_OK(encode_tmap_bf16_3d(&p.b_hi, W.h(), K, N, 1, K, (uint64_t)N * K, bk, bbox));
         TMAP_OK(encode_tmap_bf16_3d(&p.b_lo, W.l(), K, N, 1, K, (uint64_t)N * K, bk, bbox));
         p.two_cta = pair, p.block_k = bk, p.num_k_blocks = K / bk, p.kb_per_row = K / bk;
@@ -826,11 +872,13 @@ struct Plan {
     GemmParams conv[kNumConv];
     GemmParams proj, pos;
     std::vector<LayerPlan> layers;
+    GemmParams pred1;                // Distiller: Linear(D, N*D) + GELU
+    std::vector<GemmParams> pred2;   // Distiller: SplitLinear, one [D][D] GEMM per task
 };
 
 void Workspace::release() {
     DevBuf* bufs[] = {&book, &wav_stats, &wav_pad, &c0_part, &c0_ss, &conv_f32, &tmp_f32, &x_f32, &x1_f32, &gate, &pos_z,
-                      &ln_counters};
+                      &ln_counters, &hs0};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < kNumConv; ++i) act[i].release();
     SplitBuf* sb[] = {&ln512_s, &x_s, &xs_s, &q_s, &k_s, &vt_s, &ctx_s, &x1_s, &h_s};
@@ -880,11 +928,18 @@ struct Fwd {
     int fuse_ln = 0;  // fuse_ln_mode()
     unsigned int* cnt[2] = {nullptr, nullptr};  // two alternating row-block counter arrays of the fused LayerNorm
 
-    int num_stages() const { return 9 + 5 * m->cfg.num_layers; }
+    int num_stages() const {
+        return 9 + 5 * m->cfg.num_layers + (m->cfg.pred_heads > 0 ? 1 + m->cfg.pred_heads : 0);
+    }
+    bool distil() const { return m->cfg.family == 3; }
+    // Output slot i of the caller's buffer. Hidden state l (the input of layer l / the encoder output) lives in slot l —
+    // except for the distiller, whose slot 0 is feat_final and whose layer-0 input is not exposed (internal scratch).
+    float* slot(int i) const { return hidden + (size_t)i * layer_stride; }
+    float* proj_out() const { return distil() ? slot(0) : w->x_f32.as<float>(); }
     int prepare();
     int build_plan(Plan& pl);
     int stage(int s);
-    float* hs(int l) const { return hidden + (size_t)l * layer_stride; }
+    float* hs(int l) const { return (distil() && l == 0) ? w->hs0.as<float>() : slot(l); }
 };
 
 int Fwd::prepare() {
@@ -967,6 +1022,7 @@ int Fwd::prepare() {
     S3B_OK(w->h_s.ensure((size_t)M * F));
     if (posconv4_ok(c)) S3B_OK(w->pos_z.ensure((size_t)B * (T + 3) * 4 * D * sizeof(float)));
     if (c.relative_position) S3B_OK(w->gate.ensure((size_t)B * H * T * 4));
+    if (c.family == 3) S3B_OK(w->hs0.ensure((size_t)M * D * 4));
     fuse_ln = fuse_ln_mode();
     {
         const size_t n_cnt = (size_t)B * (L[1] / 128 + 2) + (size_t)M / 128 + 16;
@@ -1017,7 +1073,8 @@ int Fwd::build_plan(Plan& pl) {
             e.out_f32 = w->conv_f32.as<float>();
         } else {
             e.gelu = 1;
-            if (last) e.out_f32 = w->conv_f32.as<float>();
+            if (last && c.no_feature_layer_norm) e.op = w->ln512_s.planes(m->scheme);  // straight into post_extract_proj
+            else if (last) e.out_f32 = w->conv_f32.as<float>();
             else e.op = w->act[i].planes(m->scheme);
         }
         set_epi(p, e, C);
@@ -1130,6 +1187,29 @@ int Fwd::build_plan(Plan& pl) {
             }
         }
     }
+    if (c.pred_heads > 0) {
+        // Distiller output layer on the encoder output (operand planes xs_s): Linear(D, N*D) + GELU -> h_s, then one
+        // [D][D] GEMM per task on its D-column slice of h_s (SplitLinear, distiller/module.py:77-90)
+        const int N = c.pred_heads;
+        {
+            GemmParams& p = pl.pred1;
+            S3B_OK(linear_params(p, w->xs_s, m->pred1_w, M, N * D, D, 2, m->scheme));
+            Epi e;
+            e.bias = m->pred1_b.as<float>();
+            e.gelu = 1;
+            e.op = w->h_s.planes(m->scheme);
+            set_epi(p, e, N * D);
+        }
+        pl.pred2.resize(N);
+        for (int k = 0; k < N; ++k) {
+            GemmParams& p = pl.pred2[k];
+            S3B_OK(linear_params(p, w->h_s, m->pred2_w[k], M, D, D, 0, m->scheme, (int64_t)N * D, (size_t)k * D));
+            Epi e;
+            e.bias = m->pred2_b.as<float>() + (size_t)k * D;
+            e.out_f32 = w->tmp_f32.as<float>();  // patched per call: output slot NL + 1 + k
+            set_epi(p, e, D);
+        }
+    }
     return 0;
 }
 
@@ -1176,10 +1256,14 @@ int Fwd::stage(int s) {
     }
     if (s == 7) {
         // ---- LayerNorm(512) -> post_extract_proj (+ zero padded frames) --------------------------------------------
-        KNORM(launch_layernorm(w->conv_f32.as<float>(), (size_t)M, C, m->ln512_g.as<float>(), m->ln512_b.as<float>(),
-                               0, nullptr, w->ln512_s.planes(m->scheme), st));
+        if (!c.no_feature_layer_norm)
+            KNORM(launch_layernorm(w->conv_f32.as<float>(), (size_t)M, C, m->ln512_g.as<float>(), m->ln512_b.as<float>(),
+                                   0, nullptr, w->ln512_s.planes(m->scheme), st));
         GemmParams p = plan->proj;
+        p.out_f32 = proj_out();  // distiller: feat_final IS output slot 0 (padded frames zeroed, like the reference's
+                                 // in-place x[padding_mask] = 0 on the same storage, distiller/module.py:303-304)
         KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
+        if (distil() && layer_done) S3B_OK(layer_done(m, 0, st, user));
         return 0;
     }
     if (s == 8) {
@@ -1189,17 +1273,33 @@ int Fwd::stage(int s) {
         if (posconv4_ok(c)) {
             KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
             const bool ln = !c.layer_norm_first;
-            KNORM(launch_posconv_combine(w->pos_z.as<float>(), w->x_f32.as<float>(), m->pos_b.as<float>(), B, T, D,
+            KNORM(launch_posconv_combine(w->pos_z.as<float>(), proj_out(), m->pos_b.as<float>(), B, T, D,
                                          D / c.pos_conv_groups, m->enc_ln_g.as<float>(), m->enc_ln_b.as<float>(),
                                          ln ? 1 : 0, hs0, ln ? w->xs_s.planes(m->scheme) : no_planes(), st));
         } else {
+            p.residual = proj_out();
             if (c.layer_norm_first) p.out_f32 = hs0;
             KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
             if (!c.layer_norm_first)
                 KNORM(launch_layernorm(w->tmp_f32.as<float>(), (size_t)M, D, m->enc_ln_g.as<float>(),
                                        m->enc_ln_b.as<float>(), 0, hs0, w->xs_s.planes(m->scheme), st));
         }
-        if (layer_done) S3B_OK(layer_done(m, 0, st, user));
+        if (!distil() && layer_done) S3B_OK(layer_done(m, 0, st, user));
+        return 0;
+    }
+
+    // ---- Distiller prediction heads (after the layers) -------------------------------------------------------------
+    if (s >= 9 + 5 * NL) {
+        const int k = s - (9 + 5 * NL);  // 0: Linear + GELU, 1..N: SplitLinear task k-1
+        if (k == 0) {
+            GemmParams p = plan->pred1;
+            KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
+        } else {
+            GemmParams p = plan->pred2[k - 1];
+            p.out_f32 = slot(NL + k);
+            KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
+            if (layer_done) S3B_OK(layer_done(m, NL + k, st, user));
+        }
         return 0;
     }
 
@@ -1260,13 +1360,14 @@ int Fwd::stage(int s) {
                 if (layer_done) S3B_OK(layer_done(m, l + 1, st, user));
                 return 0;
             }
+            const bool want_planes = !last || c.pred_heads > 0;  // the next layer's (or the prediction heads') operand
             if (c.layer_norm_first) {
                 if (last)  // encoder.layer_norm on the final output (wav2vec2_model.py:3049-3050)
                     KNORM(launch_layernorm(unnorm, (size_t)M, D, m->enc_ln_g.as<float>(), m->enc_ln_b.as<float>(), 0,
-                                           hs_out, no_planes(), st));
+                                           hs_out, c.pred_heads > 0 ? w->xs_s.planes(m->scheme) : no_planes(), st));
             } else {
                 KNORM(launch_layernorm(w->tmp_f32.as<float>(), (size_t)M, D, W.ln2_g.as<float>(), W.ln2_b.as<float>(), 0,
-                                       hs_out, last ? no_planes() : w->xs_s.planes(m->scheme), st));
+                                       hs_out, want_planes ? w->xs_s.planes(m->scheme) : no_planes(), st));
             }
             if (layer_done) S3B_OK(layer_done(m, l + 1, st, user));
             return 0;
@@ -1346,12 +1447,15 @@ static int forward_lanes(s3b_model* m, const float* const* wavs, const int64_t* 
         return 0;
     };
 
-    // ---- CUDA-graph replay (S3B_GRAPHS=1) -----------------------------------------------------------------------
-    // A forward is ~100 launches per lane; at the 8-GPU shard size (2.5 ms per step) the host spends about as long
-    // enqueueing them as the GPU spends running them. When the same call (shape, buffers, stream) comes back, the
-    // whole two-lane forward is captured once and replayed with one cudaGraphLaunch; the per-call data (waveform
-    // pointers, lengths, masks) travels through the pinned bookkeeping block, which the graph's copy node re-reads.
-    // Any failure while capturing disables graphs for this model and falls back to plain enqueueing.
+    // ---- CUDA-graph replay (S3B_GRAPHS=1, experimental) ----------------------------------------------------------
+    // A forward is ~100 launches per lane (8.5 us of host time each: 1.7 ms per step at the 8-GPU shard size against
+    // 2.56 ms of GPU time, profiles/r2l_*). When the same call (shape, buffers, stream) comes back, the whole two-lane
+    // forward is captured once and replayed with one cudaGraphLaunch; the per-call data (waveform pointers, lengths,
+    // masks) travels through the pinned bookkeeping block, which the graph's copy node re-reads. Any failure while
+    // capturing disables graphs for this model and falls back to plain enqueueing — which is what happens on the
+    // measured driver (580.159 / CUDA 12.9 rejects the capture, presumably the programmatic-dependent-launch
+    // attribute of the first kernel behind a copy node); since the step is GPU-bound even at that size, the mode stays
+    // off by default and was not pursued.
     static int graphs_env = -1;
     if (graphs_env < 0) {
         const char* e = getenv("S3B_GRAPHS");
@@ -1438,12 +1542,12 @@ static int forward_host_impl(s3b_model* m, const float* const* wavs, const int64
     const size_t frame_elems = (size_t)T * m->cfg.embed_dim;
     const size_t layer_elems = (size_t)batch * frame_elems;
     if (hidden_dev == nullptr) {
-        S3B_OK(m->stage_out.ensure((size_t)(m->cfg.num_layers + 1) * layer_elems * 4));
+        S3B_OK(m->stage_out.ensure((size_t)s3b_num_outputs(m) * layer_elems * 4));
         hidden_dev = m->stage_out.as<float>();
     }
     if (m->copy_stream == nullptr) CUDA_OK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
     if (m->compute_stream == nullptr) CUDA_OK(cudaStreamCreateWithFlags(&m->compute_stream, cudaStreamNonBlocking));
-    while ((int)m->layer_events.size() < m->cfg.num_layers + 1) {
+    while ((int)m->layer_events.size() < s3b_num_outputs(m)) {
         cudaEvent_t e;
         CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         m->layer_events.push_back(e);

@@ -41,7 +41,7 @@ def _make_local_entry(family: str) -> Callable:
 ENTRIES: Dict[str, Callable] = {}
 for _name in list(ARCHS) + list(ALIASES):
     ENTRIES[_name] = _make_entry(_name)
-for _family in ("hubert", "wav2vec2", "wavlm", "unispeech_sat"):
+for _family in ("hubert", "wav2vec2", "wavlm", "unispeech_sat", "distiller"):
     ENTRIES[f"{_family}_local"] = _make_local_entry(_family)
 globals().update(ENTRIES)
 

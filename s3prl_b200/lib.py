@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = [
     "s3b_model_destroy",
     "s3b_num_frames",
     "s3b_valid_frames",
+    "s3b_num_outputs",
     "s3b_forward",
     "s3b_forward_host",
     "s3b_forward_ex",
@@ -75,7 +76,9 @@ class S3BConfig(C.Structure):
         ("num_buckets", C.c_int32),
         ("max_distance", C.c_int32),
         ("gru_rel_pos", C.c_int32),
-        ("reserved", C.c_int32 * 8),
+        ("no_feature_layer_norm", C.c_int32),
+        ("pred_heads", C.c_int32),
+        ("reserved", C.c_int32 * 6),
     ]
 
 
@@ -97,7 +100,7 @@ class S3BForwardOpts(C.Structure):
         self.struct_size = C.sizeof(S3BForwardOpts)
 
 
-FAMILY_HUBERT, FAMILY_WAV2VEC2, FAMILY_WAVLM = 0, 1, 2
+FAMILY_HUBERT, FAMILY_WAV2VEC2, FAMILY_WAVLM, FAMILY_DISTILLER = 0, 1, 2, 3
 
 _lib: Optional[C.CDLL] = None
 
@@ -128,6 +131,8 @@ def load() -> C.CDLL:
     lib.s3b_model_destroy.restype = None
     lib.s3b_num_frames.argtypes = [vp, i64]
     lib.s3b_num_frames.restype = i64
+    lib.s3b_num_outputs.argtypes = [vp]
+    lib.s3b_num_outputs.restype = i32
     lib.s3b_valid_frames.argtypes = [vp, C.POINTER(i64), i32, i64, C.POINTER(i32)]
     lib.s3b_forward.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i32, i64, f32p, vp]
     lib.s3b_forward_host.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i32, i64, f32p]

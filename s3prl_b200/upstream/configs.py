@@ -15,7 +15,7 @@ DOWNSAMPLE_RATE = 320
 
 @dataclass(frozen=True)
 class ArchConfig:
-    family: str  # "hubert" | "wav2vec2" | "wavlm"
+    family: str  # "hubert" | "wav2vec2" | "wavlm" | "distiller"
     extractor_mode: str = "default"  # "default" (GroupNorm after conv 0) | "layer_norm"
     conv_bias: bool = False
     layer_norm_first: bool = False
@@ -31,10 +31,19 @@ class ArchConfig:
     num_buckets: int = 320
     max_distance: int = 800
     gru_rel_pos: bool = False
+    # Distiller (DistilHuBERT, s3prl/upstream/distiller/model.py:17-79): no LayerNorm(512) in front of
+    # post_extract_proj, and `pred_heads` prediction heads (Linear -> GELU -> SplitLinear) on the encoder output
+    feature_layer_norm: bool = True
+    pred_heads: int = 0
 
     @property
     def family_id(self) -> int:
-        return {"hubert": 0, "wav2vec2": 1, "wavlm": 2}[self.family]
+        return {"hubert": 0, "wav2vec2": 1, "wavlm": 2, "distiller": 3}[self.family]
+
+    @property
+    def num_outputs(self) -> int:
+        """Entries of ``hidden_states``: NL+1, or feat_final + NL layer outputs + prediction heads for the distiller."""
+        return self.encoder_layers + 1 + self.pred_heads
 
 
 _BASE = ArchConfig(family="hubert")
@@ -64,6 +73,11 @@ ARCHS: Dict[str, ArchConfig] = {
     "unispeech_sat_base_plus": replace(_BASE, family="wavlm"),
     "unispeech_sat_large": replace(_BASE, family="wavlm", **_WAVLM_LARGE),
 }
+# DistilHuBERT (s3prl/upstream/distiller/hubconf.py:31-48; config of distilhubert_ls960_4-8-12: 2 layers, heads for
+# teacher layers 4 / 8 / 12)
+ARCHS["distilhubert_base"] = ArchConfig(family="distiller", encoder_layers=2, feature_layer_norm=False, pred_heads=3)
+ARCHS["distilhubert"] = ARCHS["distilhubert_base"]
+
 # Same-skeleton relatives: identical architecture, different pre-training data (only the checkpoint differs).
 for _alias, _arch in {
     # s3prl/upstream/wav2vec2/hubconf.py:123-160
@@ -104,6 +118,27 @@ def arch_from_reference_cfg(family: str, model_cfg: dict, task_cfg: dict | None 
     layers = g("conv_feature_layers", None)
     if layers is not None and list(eval(layers) if isinstance(layers, str) else layers) != CONV_LAYERS:
         raise ValueError(f"unsupported conv_feature_layers: {layers}")
+    if family == "distiller":  # DistillerConfig (distiller/model.py:17-79)
+        if g("task_emb_type", "expand-last") != "expand-last" or g("out_layer_type", "expand-last") != "expand-last":
+            raise ValueError("only the expand-last Distiller (DistilHuBERT) is supported")
+        if g("attention_type", "original") != "original" or int(g("final_dim", 768)) != int(g("encoder_embed_dim", 768)):
+            raise ValueError("unsupported Distiller variant (attention_type / final_dim)")
+        layers = g("extractor_conv_feature_layers", None)
+        if layers is not None and list(eval(layers) if isinstance(layers, str) else layers) != CONV_LAYERS:
+            raise ValueError(f"unsupported conv_feature_layers: {layers}")
+        return ArchConfig(
+            family="distiller",
+            extractor_mode=g("extractor_mode", "default"),
+            layer_norm_first=bool(g("layer_norm_first", False)),
+            encoder_layers=int(g("encoder_layers", 1)),
+            encoder_embed_dim=int(g("encoder_embed_dim", 768)),
+            encoder_ffn_embed_dim=int(g("encoder_ffn_embed_dim", 3072)),
+            encoder_attention_heads=int(g("encoder_attention_heads", 12)),
+            conv_pos=int(g("conv_pos", 128)),
+            conv_pos_groups=int(g("conv_pos_groups", 16)),
+            feature_layer_norm=False,
+            pred_heads=int(g("n_tasks", 12)),
+        )
     return ArchConfig(
         family=family,
         extractor_mode=g("extractor_mode", "default"),

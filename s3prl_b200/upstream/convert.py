@@ -56,10 +56,35 @@ def reference_model_cfg(cfg: ArchConfig) -> Dict:
     return d
 
 
+def distiller_config(cfg: ArchConfig) -> Dict:
+    """The ``Config["distiller"]`` dict of a Distiller checkpoint (DistillerConfig, distiller/model.py:17-79)."""
+    n = cfg.pred_heads
+    return dict(
+        extractor_mode=cfg.extractor_mode,
+        extractor_conv_feature_layers=str(CONV_LAYERS),
+        conv_pos=cfg.conv_pos,
+        conv_pos_groups=cfg.conv_pos_groups,
+        encoder_layers=cfg.encoder_layers,
+        encoder_embed_dim=cfg.encoder_embed_dim,
+        encoder_ffn_embed_dim=cfg.encoder_ffn_embed_dim,
+        encoder_attention_heads=cfg.encoder_attention_heads,
+        activation_fn="gelu",
+        layer_norm_first=cfg.layer_norm_first,
+        attention_type="original",
+        final_dim=cfg.encoder_embed_dim,
+        out_layer_type="expand-last",
+        n_tasks=n,
+        task_emb_type="expand-last",
+        pred_layer_id=[4 * (i + 1) for i in range(n)],
+    )
+
+
 def converted_checkpoint(cfg: ArchConfig, state_dict: Mapping[str, torch.Tensor]) -> Dict:
     """In-memory converted checkpoint of ``cfg.family``'s layout."""
-    model_cfg = reference_model_cfg(cfg)
     weights = {k: v.detach().cpu() for k, v in state_dict.items()}
+    if cfg.family == "distiller":  # distiller/builder.py:41-47,129-131
+        return {"Config": {"distiller": distiller_config(cfg)}, "Distiller": weights}
+    model_cfg = reference_model_cfg(cfg)
     if cfg.family == "wavlm":
         return {"cfg": model_cfg, "model": weights}
     out = {

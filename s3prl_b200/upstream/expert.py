@@ -53,6 +53,8 @@ def _c_config(cfg: ArchConfig) -> _lib.S3BConfig:
     c.num_buckets = cfg.num_buckets
     c.max_distance = cfg.max_distance
     c.gru_rel_pos = int(cfg.gru_rel_pos)
+    c.no_feature_layer_norm = int(not cfg.feature_layer_norm)
+    c.pred_heads = int(cfg.pred_heads)
     return c
 
 
@@ -128,6 +130,8 @@ class UpstreamExpert(nn.Module):
         # wav2vec2/expert.py:35-39: only the wav2vec 2.0 expert takes feature_selection
         if feature_selection not in _FEATURE_SELECTIONS:
             raise AssertionError(f"feature_selection must be one of {_FEATURE_SELECTIONS}, got {feature_selection!r}")
+        if self.arch.family == "distiller" and (hooks or feature_selection is not None):
+            raise TypeError("the Distiller expert takes neither hooks nor feature_selection (distiller/expert.py:18-40)")
         if feature_selection is not None and self.arch.family != "wav2vec2":
             raise TypeError(f"feature_selection is an option of the wav2vec2 experts only (got family {self.arch.family})")
         self.feature_selection = feature_selection
@@ -232,6 +236,8 @@ class UpstreamExpert(nn.Module):
         if T < 1:
             raise ValueError(f"waveforms too short ({max_len} samples): the conv stack needs >= 400 samples")
         NL, D = self.arch.encoder_layers, self.arch.encoder_embed_dim
+        if self.arch.family == "distiller":
+            return self._forward_distiller(native, wavs, lens, max_len, T)
         need_ffn = self.feature_selection == "fairseq_layers_before_residual" or bool(self.hooks)
         need_last = self.arch.layer_norm_first and (self.feature_selection == "fairseq_layers" or bool(self.hooks))
         with torch.cuda.device(device):
@@ -272,6 +278,30 @@ class UpstreamExpert(nn.Module):
             result[f"hidden_state_{i}"] = h
         return result
 
+    def _forward_distiller(self, native, wavs, lens, max_len, T) -> Dict:
+        """The Distiller expert's result dict (s3prl/upstream/distiller/expert.py:44-63): hidden_states =
+        [feat_final] + layer outputs + prediction heads, "paper" = the last layer output, "pad_mask" = frame validity."""
+        device = wavs[0].device
+        B, NL, D, n_out = len(wavs), self.arch.encoder_layers, self.arch.encoder_embed_dim, self.arch.num_outputs
+        with torch.cuda.device(device):
+            out = torch.empty((n_out, B, T, D), dtype=torch.float32, device=device)
+            ptrs = (C.c_void_p * B)(*[w.data_ptr() for w in wavs])
+            lens_c = (C.c_int64 * B)(*lens)
+            opts = _lib.S3BForwardOpts(lanes=int(self.lanes))
+            _lib.check(
+                native.lib.s3b_forward_ex(
+                    native.handle, ptrs, lens_c, B, max_len, C.c_void_p(out.data_ptr()),
+                    C.c_void_p(torch.cuda.current_stream(device).cuda_stream), C.byref(opts),
+                )
+            )
+        hidden = [out[i] for i in range(n_out)]
+        valid = torch.tensor(self.valid_frames(lens, max_len), device=device)
+        pad_mask = (torch.arange(T, device=device).unsqueeze(0) < valid.unsqueeze(1)).to(torch.float32)  # 1 = valid frame
+        result = {"last_hidden_state": hidden[-1], "hidden_states": hidden, "pad_mask": pad_mask, "paper": hidden[NL]}
+        for i, h in enumerate(hidden):
+            result[f"hidden_state_{i}"] = h
+        return result
+
     def _run_hooks(self, out: torch.Tensor, layer_out: List[torch.Tensor], ffn: torch.Tensor) -> Dict:
         """Custom ``hooks=`` (interfaces.py:74-131): every transform sees the (input, output) pair the reference's
         forward hook on that module would see — time-major [T, B, D] tensors for the encoder layers
@@ -307,7 +337,7 @@ class UpstreamExpert(nn.Module):
         B = len(wavs)
         max_len = self.global_max_len or max(lens)
         T = self.num_frames(max_len)
-        shape = (self.arch.encoder_layers + 1, B, T, self.arch.encoder_embed_dim)
+        shape = (self.arch.num_outputs, B, T, self.arch.encoder_embed_dim)
         out = getattr(self, "_host_out", None)
         if out is None or tuple(out.shape) != shape:
             # pinned result buffer, reused across calls of the same shape (valid until the next forward_host)
@@ -331,6 +361,8 @@ def _family_of(name: str) -> str:
         return get_arch(name).family
     if name.startswith("unispeech_sat"):  # the WavLM model class (s3prl/upstream/unispeech_sat/expert.py:20)
         return "wavlm"
+    if name.startswith("distil"):
+        return "distiller"
     for fam in ("hubert", "wav2vec2", "wavlm"):
         if name.startswith(fam):
             return fam

@@ -41,8 +41,9 @@ def fabricate_state_dict(cfg: ArchConfig, seed: int = 0) -> Dict[str, torch.Tens
             sd[f"{p}.2.weight"] = randn(dim, std=0.1, mean=1.0)
             sd[f"{p}.2.bias"] = randn(dim, std=0.1)
         in_d = dim
-    sd["layer_norm.weight"] = randn(in_d, std=0.1, mean=1.0)
-    sd["layer_norm.bias"] = randn(in_d, std=0.1)
+    if cfg.feature_layer_norm:
+        sd["layer_norm.weight"] = randn(in_d, std=0.1, mean=1.0)
+        sd["layer_norm.bias"] = randn(in_d, std=0.1)
     sd["post_extract_proj.weight"] = randn(D, in_d, std=1.0 / math.sqrt(in_d))
     sd["post_extract_proj.bias"] = randn(D, std=0.05)
     # pos_conv with weight_norm(dim=2): g has one entry per kernel tap
@@ -72,6 +73,12 @@ def fabricate_state_dict(cfg: ArchConfig, seed: int = 0) -> Dict[str, torch.Tens
             sd[f"{p}.self_attn.grep_a"] = randn(1, H, 1, 1, std=0.3, mean=1.0)
     if cfg.relative_position_embedding:
         sd["encoder.layers.0.self_attn.relative_attention_bias.weight"] = randn(cfg.num_buckets, H, std=0.5)
+    if cfg.pred_heads > 0:  # Distiller output_layer = Linear -> GELU -> SplitLinear (distiller/model.py:150-160, module.py:55-90)
+        N = cfg.pred_heads
+        sd["output_layer.0.weight"] = randn(N * D, D, std=1.0 / math.sqrt(D))
+        sd["output_layer.0.bias"] = randn(N * D, std=0.05)
+        sd["output_layer.2.weight"] = randn(N, D, D, std=1.0 / math.sqrt(D))  # [task][in][out]
+        sd["output_layer.2.bias"] = randn(1, 1, N, D, std=0.05)
     return sd
 
 
@@ -88,4 +95,6 @@ def load_reference_checkpoint(path: str, family: str) -> Tuple[ArchConfig, Dict[
         return cfg, state["model_weight"]
     if "cfg" in state and "model" in state:
         return arch_from_reference_cfg("wavlm", dict(state["cfg"])), state["model"]
+    if "Config" in state and "Distiller" in state:  # distiller/builder.py:41-47,129-131
+        return arch_from_reference_cfg("distiller", dict(state["Config"]["distiller"])), state["Distiller"]
     raise ValueError(f"{path}: unrecognised checkpoint layout (keys: {sorted(state)[:8]})")

@@ -138,7 +138,7 @@ def test_hub_covers_the_same_skeleton_relatives():
               "wav2vec2_large_960", "wav2vec2_large_ll60k", "wav2vec2_large_lv60_cv_swbd_fsh", "xlsr_53",
               "xls_r_300m", "wavlm_base", "wavlm_base_plus", "wavlm_large", "unispeech_sat_base",
               "unispeech_sat_base_plus", "unispeech_sat_large", "hubert_local", "wav2vec2_local", "wavlm_local",
-              "unispeech_sat_local", "fbank", "mel", "linear"):
+              "unispeech_sat_local", "distilhubert", "distilhubert_base", "distiller_local", "fbank", "mel", "linear"):
         assert n in names, n
     for n in ("xls_r_1b", "xls_r_2b", "wav2vec2_conformer_relpos"):
         assert n not in names
@@ -203,7 +203,8 @@ def test_converted_checkpoint_layouts_roundtrip(tmp_path):
     from s3prl_b200.upstream.convert import converted_checkpoint, save_converted_checkpoint
     from s3prl_b200.upstream.weights import fabricate_state_dict, load_reference_checkpoint
 
-    for name in ("hubert_base", "wav2vec2_large_ll60k", "wavlm_base_plus", "unispeech_sat_base_plus", "wavlm_large"):
+    for name in ("hubert_base", "wav2vec2_large_ll60k", "wavlm_base_plus", "unispeech_sat_base_plus", "wavlm_large",
+                 "distilhubert_base"):
         cfg = ARCHS[name]
         sd = fabricate_state_dict(cfg, 0)
         path = tmp_path / f"{name}.pt"
@@ -212,7 +213,8 @@ def test_converted_checkpoint_layouts_roundtrip(tmp_path):
         assert got_cfg == cfg, name
         assert got_sd.keys() == sd.keys() and all(torch.equal(got_sd[k], sd[k]) for k in sd)
         # the hub's *_local entry builds an expert from the file (no GPU needed until the first forward)
-        local = {"hubert": "hubert_local", "wav2vec2": "wav2vec2_local", "wavlm": "wavlm_local"}[cfg.family]
+        local = {"hubert": "hubert_local", "wav2vec2": "wav2vec2_local", "wavlm": "wavlm_local",
+                 "distiller": "distiller_local"}[cfg.family]
         e = hub.ENTRIES[local](str(path))
         assert e.arch == cfg and e.num_layers == cfg.encoder_layers
     layout = converted_checkpoint(ARCHS["hubert_base"], {})

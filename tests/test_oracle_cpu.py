@@ -48,6 +48,7 @@ def test_native_integer_rules_match_reference(s3b_lib):
         "hubert": UpstreamExpert(name="hubert_base", state_dict={}),
         "wav2vec2": UpstreamExpert(name="wav2vec2_base_960", state_dict={}),
         "wavlm": UpstreamExpert(name="wavlm_base_plus", state_dict={}),
+        "distiller": UpstreamExpert(name="distilhubert_base", state_dict={}),
     }
     for b in fx["batches"] + fx.get("short_batches", []):
         lens, T = b["lens"], b["T"]
@@ -56,6 +57,9 @@ def test_native_integer_rules_match_reference(s3b_lib):
         assert experts["hubert"].valid_frames(lens) == b["hubert_valid"]
         assert experts["wavlm"].valid_frames(lens) == b["hubert_valid"]
         assert experts["wav2vec2"].valid_frames(lens) == b["wav2vec2_valid"], lens
+        if min(lens) >= 400:  # the Distiller rule (cal_pad_mask, distiller/model.py:272-286) is pinned through the
+            # oracle, which the executed-reference golden of distilhubert_base pins (ragged case in the fixture)
+            assert experts["distiller"].valid_frames(lens) == O.valid_frames("distiller", lens, max(lens))
     assert len(fx.get("short_batches", [])) >= 10  # utterances shorter than the receptive field (mask index wraps)
 
 
@@ -162,6 +166,7 @@ def test_native_integer_rules_property(s3b_lib):
         "hubert": UpstreamExpert(name="hubert_base", state_dict={}),
         "wav2vec2": UpstreamExpert(name="wav2vec2_base_960", state_dict={}),
         "wavlm": UpstreamExpert(name="wavlm_base_plus", state_dict={}),
+        "distiller": UpstreamExpert(name="distilhubert_base", state_dict={}),
     }
     length = st.one_of(
         st.integers(min_value=400, max_value=200000),
