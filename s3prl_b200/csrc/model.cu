@@ -652,6 +652,11 @@ static int pick_pair_umma_n(int64_t M, int N, int K, int epi_kind, int sm_count,
     if (N % 256 != 0) return (N % 128 == 0) ? 128 : 0;
     const int clusters = sm_count / 2 > 0 ? sm_count / 2 : 1;
     const int64_t pairs = ((M + 127) / 128 + 1) / 2;
+    // From three rounds of 256-wide tiles on, the wide tile wins or ties for every shape of the sweep (one A tile per
+    // 256 columns, half the per-tile overheads); the model below over-rates the epilogue there and is only consulted
+    // for small problems. (ncu r2m caught the unrestricted model picking 128-wide tiles for QKV / fc1 at M = 16 k:
+    // +13 % / +19 % on those launches.)
+    if ((pairs * (N / 256) + clusters - 1) / clusters >= 3) return 256;
     const double epi128 = epi_kind == 2 ? 13500.0 : (epi_kind == 1 ? 11000.0 : 8800.0);
     int best = 256;
     double best_cost = 1e30;
