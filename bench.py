@@ -497,12 +497,20 @@ def run_ours(args):
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
     flops_utt, _ = algorithmic_flops_per_utt(cfg, L)
     lanes_used = int(os.environ.get("S3B_LANES", "2")) if args.lanes is None else args.lanes
+    scheme = os.environ.get("S3B_GEMM_SCHEME", "f16q8")  # the library's default (model.cu S3B_DEFAULT_SCHEME)
+    if scheme in ("1", "f16q8"):
+        scheme, slots = "f16q8", 2.0
+        dtype = "f32 (fp16 product + two e4m3 correction products = 2 MMA slots per 16 of K, fp32 TMEM accumulate)"
+    else:
+        scheme, slots = "bf16x3", 3.0
+        dtype = "f32 (bf16 hi+lo split operands x3 MMAs, fp32 TMEM accumulate)"
     line = {
         "metric": metric_name(args.config), "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32 (bf16 hi+lo split operands x3 MMAs, fp32 TMEM accumulate)", "data": "synthetic",
+        "vs_baseline": None, "dtype": dtype, "data": "synthetic",
         "config": {
             "workload": workload_name(args.config, world),
+            "operand_scheme": scheme,
             "frames_per_step": frames_step,
             "l2": "activations and outputs (>= 0.64 GB of hidden states per step) exceed the 126 MB L2",
             "alg_tflop_per_step": flops_utt * GLOBAL_BATCH / 1e12,
@@ -512,11 +520,11 @@ def run_ours(args):
         },
         "whole_step_tflops": flops_utt * GLOBAL_BATCH / 1e12 / (ms_step * 1e-3),
         "roofline": {
-            "kernel": "gemm2_bf16x3_kernel (tcgen05 cta_group::2, all GEMM launches of a step)", "bound": "tensor",
+            "kernel": "gemm2_kernel (tcgen05 cta_group::2, all GEMM launches of a step)", "bound": "tensor",
             "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tflops / peak_tf,
             "traffic": gemm_traffic(), "peak_source": peak_src,
-            "mma_pipe_tflops": 3.0 * gemm_tflops,
-            "note": "achieved = algorithmic FLOPs (1 MMA per product; the tensor pipe executes 3 bf16 MMAs per product = mma_pipe_tflops) / CUDA-event time per launch in a profiled pass of the same steps (lanes run one after the other there so that every kernel is timed alone at its production shape), rank 0; traffic = bytes per launch (ncu, profiles/)",
+            "mma_pipe_tflops": slots * gemm_tflops,
+            "note": "achieved = algorithmic FLOPs (1 MMA per product; the tensor pipe spends `slots` bf16-rate MMA slots per product: 3 for bf16x3, 2 for f16q8 = mma_pipe_tflops; pos_conv always runs bf16x3) / CUDA-event time per launch in a profiled pass of the same steps (lanes run one after the other there so that every kernel is timed alone at its production shape), rank 0; traffic = bytes per launch (ncu, profiles/)",
         },
         "kernel_breakdown": breakdown,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d * world,
