@@ -22,7 +22,7 @@ typedef struct s3b_model s3b_model;
  * Wav2Vec2Config (s3prl/upstream/wav2vec2/wav2vec2_model.py:2103-2350) and
  * WavLMConfig (s3prl/upstream/wavlm/WavLM.py:162-245) that the extraction forward reads. */
 typedef struct s3b_config {
-    int32_t family;               /* 0 = hubert, 1 = wav2vec2, 2 = wavlm, 3 = distiller (selects the frame-mask rule) */
+    int32_t family;               /* 0 = hubert, 1 = wav2vec2 and data2vec, 2 = wavlm, 3 = distiller (selects the frame-mask rule) */
     int32_t extractor_layer_norm; /* 0: extractor_mode "default" (GroupNorm after conv 0); 1: "layer_norm" */
     int32_t conv_bias;            /* conv_bias */
     int32_t layer_norm_first;     /* pre-LN transformer (large_ll60k, wavlm_large) */
@@ -31,7 +31,7 @@ typedef struct s3b_config {
     int32_t embed_dim;            /* encoder_embed_dim (multiple of 128) */
     int32_t ffn_dim;              /* encoder_ffn_embed_dim */
     int32_t num_heads;            /* encoder_attention_heads; head dim must be 64 */
-    int32_t pos_conv_kernel;      /* conv_pos (128) */
+    int32_t pos_conv_kernel;      /* conv_pos (128; data2vec 95) */
     int32_t pos_conv_groups;      /* conv_pos_groups (16) */
     int32_t relative_position;    /* WavLM relative_position_embedding */
     int32_t num_buckets;          /* WavLM num_buckets (320) */
@@ -40,7 +40,10 @@ typedef struct s3b_config {
     /* Distiller / DistilHuBERT (s3prl/upstream/distiller/model.py:81-269): */
     int32_t no_feature_layer_norm; /* 1: post_extract_proj takes the conv features directly (no LayerNorm(512)) */
     int32_t pred_heads;            /* n_tasks prediction heads Linear -> GELU -> SplitLinear on the encoder output (0: none) */
-    int32_t reserved[6];
+    int32_t pos_conv_depth;        /* 0 / 1: one weight-normed conv of pos_conv_kernel taps (make_conv_pos); > 1 (data2vec):
+                                      that many blocks Conv1d(k) -> LayerNorm(no affine) -> GELU with
+                                      k = max(3, pos_conv_kernel / pos_conv_depth) (wav2vec2_model.py:2995-3026) */
+    int32_t reserved[5];
 } s3b_config;
 
 /* Library / error ------------------------------------------------------------------------------ */

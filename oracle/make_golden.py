@@ -43,6 +43,8 @@ CASES = {
     "unispeech_sat_base_plus": ([[16000, 12345, 800], [8000, 8000]], 7),
     "unispeech_sat_large": ([[12000, 7001]], 13),
     "distilhubert_base": ([[16000, 12345, 3200], [8000, 8000]], 7),
+    "data2vec_base_960": ([[16000, 12345, 800], [8000, 8000]], 7),
+    "data2vec_large_ll60k": ([[12000, 7001]], 13),
 }
 
 

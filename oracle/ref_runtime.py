@@ -79,6 +79,18 @@ def reference_expert(name: str, sd):
                 {"task_cfg": task_cfg, "model_cfg": model_cfg, "model_weight": full, "dictionaries_symbols": symbols},
                 tmp.name,
             )
+        elif cfg.family == "data2vec":
+            from s3prl.upstream.data2vec.data2vec_model import Data2VecAudioConfig, Data2VecAudioModel
+            from s3prl.upstream.data2vec.expert import UpstreamExpert
+            from s3prl.upstream.utils import merge_with_parent
+
+            task_cfg = dict(normalize=cfg.normalize, sample_rate=16000)
+            skeleton = Data2VecAudioModel(merge_with_parent(Data2VecAudioConfig, model_cfg))
+            skeleton.remove_pretraining_modules()  # what load_converted_model does before load_state_dict
+            full = skeleton.state_dict()
+            full.update(sd)
+            full["_ema"] = {}  # deleted unconditionally by the reference loader (data2vec/convert.py:48-49)
+            torch.save({"task_cfg": task_cfg, "model_cfg": model_cfg, "model_weight": full}, tmp.name)
         elif cfg.family == "wav2vec2":
             from s3prl.upstream.utils import merge_with_parent
             from s3prl.upstream.wav2vec2.expert import UpstreamExpert

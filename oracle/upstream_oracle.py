@@ -69,7 +69,8 @@ def valid_frames(family: str, lens: Sequence[int], max_len: int) -> List[int]:
     if family == "distiller":
         return distiller_valid_frames(lens, T)
     sm = sample_padding_mask(lens, max_len)
-    fm = frame_padding_mask_conv_length(sm, T) if family == "wav2vec2" else frame_padding_mask_chunk_all(sm, T)
+    conv_rule = family in ("wav2vec2", "data2vec")  # data2vec_model.py:455-476 repeats the wav2vec 2.0 rule
+    fm = frame_padding_mask_conv_length(sm, T) if conv_rule else frame_padding_mask_chunk_all(sm, T)
     if fm is None:
         return [T] * len(lens)
     return [int((~row).sum()) for row in fm]
@@ -141,6 +142,22 @@ def positional_conv(x: torch.Tensor, sd: Dict[str, torch.Tensor], groups: int) -
     return F.gelu(y).transpose(1, 2)
 
 
+def positional_conv_blocks(x: torch.Tensor, sd: Dict[str, torch.Tensor], groups: int, depth: int) -> torch.Tensor:
+    """data2vec (pos_conv_depth > 1): x: [B, T, D] -> depth x [Conv1d(k, padding k // 2, groups) -> SamePad(k) ->
+    LayerNorm over the channels without affine -> GELU] (make_conv_block, wav2vec2_model.py:2995-3026). Nothing is
+    re-masked between the blocks."""
+    y = x.transpose(1, 2)
+    for i in range(depth):
+        w = sd[f"encoder.pos_conv.{i}.0.weight"]
+        k = w.size(2)
+        y = F.conv1d(y, w, sd[f"encoder.pos_conv.{i}.0.bias"], padding=k // 2, groups=groups)
+        if k % 2 == 0:
+            y = y[:, :, :-1]
+        y = F.layer_norm(y.transpose(1, 2), (y.size(1),), None, None, 1e-5).transpose(1, 2)
+        y = F.gelu(y)
+    return y.transpose(1, 2)
+
+
 def self_attention(
     x: torch.Tensor,
     sd: Dict[str, torch.Tensor],
@@ -200,6 +217,7 @@ def upstream_forward(
     encoder_attention_heads, conv_pos_groups, relative_position_embedding, num_buckets, max_distance, gru_rel_pos).
 
     Follows HubertModel.forward (hubert_model.py:466-513), Wav2Vec2Model.forward (wav2vec2_model.py:2638-2684),
+    Data2VecAudioModel.forward with features_only (data2vec_model.py:428-560: the wav2vec 2.0 steps, no masking),
     WavLM.extract_features (WavLM.py:351-405), TransformerEncoder.extract_features (wav2vec2_model.py:3054-3121;
     WavLM.py:599-645) and the layer forward (wav2vec2_model.py:3260-3322; WavLM.py:709-774). The reference's
     pad-to-multiple-of-2 column (wav2vec2_model.py:3073-3082) is a masked key whose query row is discarded by
@@ -217,14 +235,18 @@ def upstream_forward(
     feats = feats.transpose(1, 2)
     T = feats.size(1)
     feats = F.layer_norm(feats, (feats.size(-1),), sd["layer_norm.weight"], sd["layer_norm.bias"], 1e-5)
-    if cfg.family == "wav2vec2":
+    if cfg.family in ("wav2vec2", "data2vec"):
         pad = frame_padding_mask_conv_length(sample_mask, T)
     else:
         pad = frame_padding_mask_chunk_all(sample_mask, T)
     h = F.linear(feats, sd["post_extract_proj.weight"], sd["post_extract_proj.bias"])
     if pad is not None:
         h = h.masked_fill(pad.unsqueeze(-1), 0.0)
-    h = h + positional_conv(h, sd, cfg.conv_pos_groups)
+    depth = int(getattr(cfg, "pos_conv_depth", 1))
+    if depth > 1:
+        h = h + positional_conv_blocks(h, sd, cfg.conv_pos_groups, depth)
+    else:
+        h = h + positional_conv(h, sd, cfg.conv_pos_groups)
     if not cfg.layer_norm_first:
         h = F.layer_norm(h, (h.size(-1),), sd["encoder.layer_norm.weight"], sd["encoder.layer_norm.bias"], 1e-5)
 

@@ -29,7 +29,7 @@ cudaError_t launch_layernorm(const float* x, size_t M, int D, const float* gamma
                              float* out_f32, const OutPlanes& op, cudaStream_t s);
 // out[m] = sum_l w[l] * hs[l][m]   (Featurizer._weighted_sum, interfaces.py:217-248; w already softmaxed)
 cudaError_t launch_posconv_combine(const float* z, const float* x, const float* bias, int B, int T, int D, int cpg,
-                                   const float* gamma, const float* beta, int do_ln, float* out_f32,
+                                   const float* gamma, const float* beta, int do_ln, int mode, float* out_f32,
                                    const OutPlanes& op, cudaStream_t s);
 cudaError_t launch_weighted_sum(const float* hs, int NL, size_t n_per_layer, const float* w, float* out,
                                 cudaStream_t s);

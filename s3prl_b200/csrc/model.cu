@@ -197,6 +197,8 @@ struct s3b_model {
     DevBuf conv_b[kNumConv], conv_ln_g[kNumConv], conv_ln_b[kNumConv];
     DevBuf ln512_g, ln512_b, proj_b, pos_b, enc_ln_g, enc_ln_b;
     SplitBuf proj_w, pos_w, pos_w4;  // pos_w4: four-taps-per-k-block layout (posconv4_params)
+    std::vector<SplitBuf> posd_w4;      // data2vec (pos_conv_depth > 1): one four-taps layout per conv block
+    std::vector<DevBuf> posd_b;         //                                 and its bias
     SplitBuf pred1_w;                   // Distiller output_layer.0.weight [N*D][D]
     std::vector<SplitBuf> pred2_w;      // Distiller output_layer.2.weight, per task, transposed to [D out][D in]
     DevBuf pred1_b, pred2_b;            // biases [N*D]
@@ -265,6 +267,10 @@ static int upload_vec(s3b_model* m, const std::string& k, int64_t n, DevBuf& dst
     return upload_f32(dst, t->data.data(), (size_t)n);
 }
 
+static int pairs_enabled();
+static int pos_taps(const s3b_config& c);
+static int pos_taps4(const s3b_config& c);
+
 static int64_t conv_out_len(int64_t L, int i) { return L < kConvK[i] ? 0 : (L - kConvK[i]) / kConvS[i] + 1; }
 
 static int64_t num_frames(int64_t L) {
@@ -305,7 +311,12 @@ extern "C" int s3b_model_create(const s3b_config* cfg, s3b_model** out) {
     if (cfg->embed_dim % cfg->pos_conv_groups != 0) return fail("embed_dim %% pos_conv_groups != 0");
     const int cpg = cfg->embed_dim / cfg->pos_conv_groups;
     if (cpg % 16 != 0 || cpg > 64) return fail("channels per pos_conv group must be a multiple of 16, <= 64");
-    if (cfg->pos_conv_kernel % 2 != 0) return fail("pos_conv_kernel must be even");
+    if (cfg->pos_conv_depth < 0 || cfg->pos_conv_depth > 8) return fail("pos_conv_depth out of range (0..8)");
+    if (cfg->pos_conv_depth <= 1 && cfg->pos_conv_kernel % 2 != 0) return fail("pos_conv_kernel must be even");
+    if (cfg->pos_conv_depth > 1 && (cfg->pos_conv_kernel < 3 || (4 * cpg != 192 && 4 * cpg != 256)))
+        return fail("pos_conv_depth > 1 needs 48 or 64 channels per group");
+    if (cfg->pos_conv_depth > 1 && cfg->family != 1)
+        return fail("pos_conv_depth > 1 (data2vec) goes with the wav2vec2 family (1)");
     if (cfg->num_layers < 1 || cfg->num_layers > 63) return fail("num_layers out of range");
     if (cfg->family < 0 || cfg->family > 3) return fail("family must be 0 (hubert), 1 (wav2vec2), 2 (wavlm) or 3 (distiller)");
     if (cfg->pred_heads < 0 || cfg->pred_heads > 12 || cfg->pred_heads * cfg->embed_dim > cfg->ffn_dim)
@@ -344,6 +355,8 @@ extern "C" void s3b_model_destroy(s3b_model* m) {
     SplitBuf* sb[] = {&m->proj_w, &m->pos_w, &m->pos_w4, &m->pred1_w};
     for (SplitBuf* b : sb) b->release();
     for (SplitBuf& b : m->pred2_w) b.release();
+    for (SplitBuf& b : m->posd_w4) b.release();
+    for (DevBuf& b : m->posd_b) b.release();
     m->pred1_b.release(), m->pred2_b.release();
     for (LayerW& l : m->layers) {
         l.qkv.release(), l.out.release(), l.fc1.release(), l.fc2.release();
@@ -426,9 +439,33 @@ extern "C" int s3b_model_finalize(s3b_model* m) {
     S3B_OK(need(m, "post_extract_proj.weight", {D, C}, &t));
     S3B_OK(upload_split(m->proj_w, t->data.data(), t->numel(), m->scheme));
     S3B_OK(upload_vec(m, "post_extract_proj.bias", D, m->proj_b));
+    // ---- data2vec pos_conv: pos_conv_depth plain Conv1d(k, padding k/2, groups) blocks (make_conv_block,
+    //      wav2vec2_model.py:2995-3026). Four taps per k-block like pos_w4 below, the tap count rounded up to a
+    //      multiple of four with zero taps: B operand [group*K4/4 + q][n = j*cpg + co][64 (zero padded)], tap = 4q + j
+    if (c.pos_conv_depth > 1) {
+        if (!pairs_enabled()) return fail("pos_conv_depth > 1 runs on the CTA-pair GEMM only (S3B_GEMM_PAIR=0 is set)");
+        const int G = c.pos_conv_groups, cpg = D / G, Kp = pos_taps(c), K4 = pos_taps4(c);
+        m->posd_w4.resize(c.pos_conv_depth);
+        m->posd_b.resize(c.pos_conv_depth);
+        for (int i = 0; i < c.pos_conv_depth; ++i) {
+            const std::string pre = "encoder.pos_conv." + std::to_string(i) + ".0.";
+            const HostTensor* tw;
+            S3B_OK(need(m, pre + "weight", {D, cpg, Kp}, &tw));
+            std::vector<float> w4((size_t)G * K4 * cpg * 64, 0.0f);
+            for (int g = 0; g < G; ++g)
+                for (int k = 0; k < Kp; ++k)
+                    for (int n = 0; n < cpg; ++n)
+                        for (int ci = 0; ci < cpg; ++ci) {
+                            const int o = g * cpg + n, q = k / 4, j = k % 4;
+                            w4[((((size_t)g * (K4 / 4) + q) * 4 + j) * cpg + n) * 64 + ci] =
+                                tw->data[((size_t)o * cpg + ci) * Kp + k];
+                        }
+            S3B_OK(upload_split(m->posd_w4[i], w4.data(), w4.size()));
+            S3B_OK(upload_vec(m, pre + "bias", D, m->posd_b[i]));
+        }
+    } else {
     // ---- pos_conv: fold weight_norm(dim=2): W[o][c][k] = g[k] * v[o][c][k] / ||v[:,:,k]||  ---------------
     //      (make_conv_pos, wav2vec2_model.py:2937-2953). GEMM B operand: [group*Kp + tap][n = cpg][64 (zero padded)]
-    {
         const int G = c.pos_conv_groups, cpg = D / G, Kp = c.pos_conv_kernel;
         const HostTensor *tg, *tv;
         S3B_OK(need(m, "encoder.pos_conv.0.weight_g", {1, 1, Kp}, &tg));
@@ -765,6 +802,13 @@ static int conv_params(GemmParams& p, const SplitBuf& A, const SplitBuf& W, int 
     return 0;
 }
 
+// taps of ONE positional conv: conv_pos, or max(3, conv_pos / depth) for the data2vec blocks
+// (wav2vec2_model.py:2996-2998); pos_taps4 = rounded up to the four-taps-per-k-block layout (zero taps appended)
+static int pos_taps(const s3b_config& c) {
+    return c.pos_conv_depth > 1 ? std::max(3, c.pos_conv_kernel / c.pos_conv_depth) : c.pos_conv_kernel;
+}
+static int pos_taps4(const s3b_config& c) { return (pos_taps(c) + 3) / 4 * 4; }
+
 // grouped positional conv: one k-block per tap; A row coordinate = t + tap - K/2 (TMA zero-fills t<0, t>=T)
 static int posconv_params(GemmParams& p, const s3b_config& c, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo,
                           const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int B, int T) {
@@ -790,13 +834,14 @@ static int posconv_params(GemmParams& p, const s3b_config& c, const __nv_bfloat1
 // column blocks are re-aligned by posconv_combine_kernel (norm.cu). Rows u in [0, T+3) per utterance.
 static bool posconv4_ok(const s3b_config& c) {
     const int cpg = c.embed_dim / c.pos_conv_groups;
+    if (c.pos_conv_depth > 1) return true;  // the only formulation of the data2vec blocks (checked at create / finalize)
     return pairs_enabled() && c.pos_conv_kernel % 4 == 0 && (4 * cpg == 192 || 4 * cpg == 256) &&
            getenv("S3B_POSCONV1") == nullptr;
 }
 static int posconv4_params(GemmParams& p, const s3b_config& c, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo,
                            const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int B, int T) {
     memset(&p, 0, sizeof(p));
-    const int D = c.embed_dim, G = c.pos_conv_groups, cpg = D / G, Kq = c.pos_conv_kernel / 4, un = 4 * cpg;
+    const int D = c.embed_dim, G = c.pos_conv_groups, cpg = D / G, Kq = pos_taps4(c) / 4, un = 4 * cpg;
     TMAP_OK(encode_tmap_bf16_3d(&p.a_hi, x_hi, D, T, B, D, (uint64_t)T * D, 64, 128));
     TMAP_OK(encode_tmap_bf16_3d(&p.a_lo, x_lo, D, T, B, D, (uint64_t)T * D, 64, 128));
     TMAP_OK(encode_tmap_bf16_3d(&p.b_hi, w_hi, 64, un, (uint64_t)G * Kq, 64, (uint64_t)un * 64, 64, un / 2));
@@ -804,10 +849,10 @@ static int posconv4_params(GemmParams& p, const s3b_config& c, const __nv_bfloat
     p.two_cta = 1;
     p.batches = B, p.rows_per_batch = T + 3, p.tiles_m_per_batch = (T + 3 + 127) / 128;
     p.n_tiles = G, p.umma_n = un, p.block_k = 64, p.num_k_blocks = Kq, p.kb_per_row = 1;
-    p.a_row_step = 4, p.a_row_off = -(c.pos_conv_kernel / 2), p.a_k_per_ntile = cpg, p.b_n_tiled = 0, p.b_z_per_ntile = Kq;
+    p.a_row_step = 4, p.a_row_off = -(pos_taps(c) / 2), p.a_k_per_ntile = cpg, p.b_n_tiled = 0, p.b_z_per_ntile = Kq;
     p.out_rows_per_batch = T + 3;
     p.k_steps = (cpg + 15) / 16;  // 48 channels per group: the 4th k-step of every 64-wide box has zero weights
-    p.alg_flops = 2.0 * (double)B * T * D * cpg * c.pos_conv_kernel;
+    p.alg_flops = 2.0 * (double)B * T * D * cpg * pos_taps(c);
     return 0;
 }
 
@@ -879,6 +924,7 @@ struct Plan {
     int fuse_ln = 0;
     GemmParams conv[kNumConv];
     GemmParams proj, pos;
+    GemmParams pos_d[8];             // data2vec: one four-taps GEMM per conv block (pos_conv_depth <= 8)
     std::vector<LayerPlan> layers;
     GemmParams pred1;                // Distiller: Linear(D, N*D) + GELU
     std::vector<GemmParams> pred2;   // Distiller: SplitLinear, one [D][D] GEMM per task
@@ -1100,7 +1146,17 @@ int Fwd::build_plan(Plan& pl) {
         e.op = w->x_s.planes(0);  // operand of pos_conv, which stays on the bf16x3 kernel (48-channel groups)
         set_epi(p, e, D);
     }
-    {
+    if (c.pos_conv_depth > 1) {
+        // block i reads the operand planes block i-1 wrote (x_s -> x1_s -> ctx_s -> x1_s ...; both are free here)
+        for (int i = 0; i < c.pos_conv_depth; ++i) {
+            const SplitBuf& in = i == 0 ? w->x_s : ((i & 1) ? w->x1_s : w->ctx_s);
+            GemmParams& p = pl.pos_d[i];
+            S3B_OK(posconv4_params(p, c, in.h(), in.l(), m->posd_w4[i].h(), m->posd_w4[i].l(), B, T));
+            Epi e;
+            e.out_f32 = w->pos_z.as<float>();
+            set_epi(p, e, 4 * D);
+        }
+    } else {
         GemmParams& p = pl.pos;
         if (posconv4_ok(c)) {
             S3B_OK(posconv4_params(p, c, w->x_s.h(), w->x_s.l(), m->pos_w4.h(), m->pos_w4.l(), B, T));
@@ -1278,12 +1334,25 @@ int Fwd::stage(int s) {
         // ---- x = x + GELU(pos_conv(x)) ; post-LN models: LayerNorm -> hidden state 0 -------------------------------
         GemmParams p = plan->pos;
         float* hs0 = hs(0);
-        if (posconv4_ok(c)) {
+        if (c.pos_conv_depth > 1) {
+            // data2vec: x_{i+1} = GELU(LayerNorm_noaffine(conv_i(x_i) + b_i)), x = x + x_depth (wav2vec2_model.py:3000-3019,
+            // 3064-3067). Padded frames are NOT re-zeroed between the blocks (the reference does not either).
+            const bool ln = !c.layer_norm_first;
+            for (int i = 0; i < c.pos_conv_depth; ++i) {
+                const bool last = (i == c.pos_conv_depth - 1);
+                KGEMM(launch_gemm_bf16x3(plan->pos_d[i], m->sm_count, st));
+                const SplitBuf& nxt = (i & 1) ? w->ctx_s : w->x1_s;  // == the `in` of block i+1 in build_plan
+                KNORM(launch_posconv_combine(w->pos_z.as<float>(), last ? proj_out() : nullptr, m->posd_b[i].as<float>(), B,
+                                             T, D, D / c.pos_conv_groups, m->enc_ln_g.as<float>(), m->enc_ln_b.as<float>(),
+                                             last && ln ? 1 : 0, last ? 2 : 1, last ? hs0 : nullptr,
+                                             last ? (ln ? w->xs_s.planes(m->scheme) : no_planes()) : nxt.planes(0), st));
+            }
+        } else if (posconv4_ok(c)) {
             KGEMM(launch_gemm_bf16x3(p, m->sm_count, st));
             const bool ln = !c.layer_norm_first;
             KNORM(launch_posconv_combine(w->pos_z.as<float>(), proj_out(), m->pos_b.as<float>(), B, T, D,
                                          D / c.pos_conv_groups, m->enc_ln_g.as<float>(), m->enc_ln_b.as<float>(),
-                                         ln ? 1 : 0, hs0, ln ? w->xs_s.planes(m->scheme) : no_planes(), st));
+                                         ln ? 1 : 0, 0, hs0, ln ? w->xs_s.planes(m->scheme) : no_planes(), st));
         } else {
             p.residual = proj_out();
             if (c.layer_norm_first) p.out_f32 = hs0;

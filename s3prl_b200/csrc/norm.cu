@@ -74,13 +74,16 @@ cudaError_t launch_layernorm(const float* x, size_t M, int D, const float* gamma
 // and the four column blocks are re-aligned here:  conv[t] = sum_j Z_j[t + j]. One warp per frame:
 //   y = x + GELU(conv + bias)                      (wav2vec2_model.py:3064-3067)
 //   post-LN models: y -> LayerNorm -> hidden state 0 (fp32) + bf16 hi/lo   (wav2vec2_model.py:3069-3070)
+// mode 0: the above. mode 1 / 2 (data2vec conv blocks, pos_conv_depth > 1; taps rounded up to a multiple of four):
+//   y = GELU(LayerNorm_noaffine(conv + bias))      (wav2vec2_model.py:3000-3019); mode 2 (last block): y = x + y, then
+//   the optional encoder LayerNorm as in mode 0.
 // z: [B][T + 3][G][4][cpg] fp32
 // ------------------------------------------------------------------------------------------------
 template <int V4>
 __global__ void __launch_bounds__(256) posconv_combine_kernel(const float* __restrict__ z, const float* __restrict__ x,
                                                               const float* __restrict__ bias, int B, int T, int cpg,
                                                               const float* __restrict__ gamma,
-                                                              const float* __restrict__ beta, int do_ln,
+                                                              const float* __restrict__ beta, int do_ln, int mode,
                                                               float* __restrict__ out_f32, const OutPlanes op) {
     constexpr int D = V4 * 128;
     const int lane = threadIdx.x & 31;
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(256) posconv_combine_kernel(const float* __res
     pdl_launch_dependents();
     if (row >= (size_t)B * T) return;
     const int b = (int)(row / T), t = (int)(row - (size_t)b * T);
-    const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+    const float4* xr = reinterpret_cast<const float4*>(x + (mode == 1 ? 0 : row * D));  // mode 1 has no residual
     const float4* b4 = reinterpret_cast<const float4*>(bias);
     float4 v[V4];
     float s = 0.f;
@@ -104,14 +107,47 @@ __global__ void __launch_bounds__(256) posconv_combine_kernel(const float* __res
                 z + ((size_t)b * (T + 3) + t + j) * (size_t)(4 * D) + (size_t)g * 4 * cpg + j * cpg + co));
             acc.x += zz.x, acc.y += zz.y, acc.z += zz.z, acc.w += zz.w;
         }
-        const float4 bb = __ldg(b4 + lane + 32 * i), xx = xr[lane + 32 * i];
-        v[i].x = xx.x + gelu_erf(acc.x + bb.x);
-        v[i].y = xx.y + gelu_erf(acc.y + bb.y);
-        v[i].z = xx.z + gelu_erf(acc.z + bb.z);
-        v[i].w = xx.w + gelu_erf(acc.w + bb.w);
+        const float4 bb = __ldg(b4 + lane + 32 * i);
+        if (mode == 0) {
+            const float4 xx = xr[lane + 32 * i];
+            v[i].x = xx.x + gelu_erf(acc.x + bb.x);
+            v[i].y = xx.y + gelu_erf(acc.y + bb.y);
+            v[i].z = xx.z + gelu_erf(acc.z + bb.z);
+            v[i].w = xx.w + gelu_erf(acc.w + bb.w);
+        } else {
+            v[i] = make_float4(acc.x + bb.x, acc.y + bb.y, acc.z + bb.z, acc.w + bb.w);
+        }
         s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
     float mean = 0.f, rstd = 1.f;
+    if (mode != 0) {
+        // data2vec block: LayerNorm over the channels without affine, then GELU (wav2vec2_model.py:3012-3015); the
+        // last block (mode 2) adds the residual x afterwards (:3064-3067)
+        mean = warp_sum(s) * (1.0f / D);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < V4; ++i) {
+            const float a = v[i].x - mean, bq = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            q += (a * a + bq * bq) + (c * c + d * d);
+        }
+        rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+        s = 0.f;
+#pragma unroll
+        for (int i = 0; i < V4; ++i) {
+            float4 y;
+            y.x = gelu_erf((v[i].x - mean) * rstd);
+            y.y = gelu_erf((v[i].y - mean) * rstd);
+            y.z = gelu_erf((v[i].z - mean) * rstd);
+            y.w = gelu_erf((v[i].w - mean) * rstd);
+            if (mode == 2) {
+                const float4 xx = xr[lane + 32 * i];
+                y.x += xx.x, y.y += xx.y, y.z += xx.z, y.w += xx.w;
+            }
+            v[i] = y;
+            s += (y.x + y.y) + (y.z + y.w);
+        }
+        mean = 0.f, rstd = 1.f;
+    }
     if (do_ln) {
         mean = warp_sum(s) * (1.0f / D);
         float q = 0.f;
@@ -140,7 +176,7 @@ __global__ void __launch_bounds__(256) posconv_combine_kernel(const float* __res
 }
 
 cudaError_t launch_posconv_combine(const float* z, const float* x, const float* bias, int B, int T, int D, int cpg,
-                                   const float* gamma, const float* beta, int do_ln, float* out_f32,
+                                   const float* gamma, const float* beta, int do_ln, int mode, float* out_f32,
                                    const OutPlanes& op, cudaStream_t s) {
     const size_t M = (size_t)B * T;
     if (M == 0) return cudaSuccess;
@@ -148,7 +184,7 @@ cudaError_t launch_posconv_combine(const float* z, const float* x, const float* 
     const unsigned blocks = (unsigned)((M + 7) / 8);
 #define S3B_PC(V)                                                                                                   \
     return launch_pdl(posconv_combine_kernel<V>, dim3(blocks), dim3(256), 0, s, z, x, bias, B, T, cpg, gamma, beta, \
-                      do_ln, out_f32, op)
+                      do_ln, mode, out_f32, op)
     switch (D) {
         case 512: S3B_PC(4);
         case 768: S3B_PC(6);

@@ -5,7 +5,7 @@ The reference resolves an upstream as ``getattr(s3prl.hub, NAME)(ckpt=..., model
 download a pretrained file first (e.g. hubert/hubconf.py:85-95). Here every entry returns the B200-native
 ``UpstreamExpert``; without ``ckpt`` (no network on this box) it uses the deterministic fabricated checkpoint of
 that architecture, with ``ckpt`` it reads a converted reference checkpoint (``*_local`` entries,
-hubert/hubconf.py:69-70, wav2vec2/hubconf.py:68-69, wavlm/hubconf.py:19-25).
+hubert/hubconf.py:69-70, wav2vec2/hubconf.py:68-69, wavlm/hubconf.py:19-25, data2vec/hubconf.py:17-18).
 
 ``install(hub_module)`` injects the entries into ``s3prl.hub`` so that ``run_downstream.py -u hubert_base`` uses
 this implementation with the reference tree untouched.
@@ -41,7 +41,7 @@ def _make_local_entry(family: str) -> Callable:
 ENTRIES: Dict[str, Callable] = {}
 for _name in list(ARCHS) + list(ALIASES):
     ENTRIES[_name] = _make_entry(_name)
-for _family in ("hubert", "wav2vec2", "wavlm", "unispeech_sat", "distiller"):
+for _family in ("hubert", "wav2vec2", "wavlm", "unispeech_sat", "distiller", "data2vec"):
     ENTRIES[f"{_family}_local"] = _make_local_entry(_family)
 globals().update(ENTRIES)
 

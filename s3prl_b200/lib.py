@@ -78,7 +78,8 @@ class S3BConfig(C.Structure):
         ("gru_rel_pos", C.c_int32),
         ("no_feature_layer_norm", C.c_int32),
         ("pred_heads", C.c_int32),
-        ("reserved", C.c_int32 * 6),
+        ("pos_conv_depth", C.c_int32),
+        ("reserved", C.c_int32 * 5),
     ]
 
 

@@ -15,7 +15,7 @@ DOWNSAMPLE_RATE = 320
 
 @dataclass(frozen=True)
 class ArchConfig:
-    family: str  # "hubert" | "wav2vec2" | "wavlm" | "distiller"
+    family: str  # "hubert" | "wav2vec2" | "wavlm" | "distiller" | "data2vec"
     extractor_mode: str = "default"  # "default" (GroupNorm after conv 0) | "layer_norm"
     conv_bias: bool = False
     layer_norm_first: bool = False
@@ -26,6 +26,9 @@ class ArchConfig:
     encoder_attention_heads: int = 12
     conv_pos: int = 128
     conv_pos_groups: int = 16
+    # data2vec (Wav2Vec2Config.pos_conv_depth, wav2vec2_model.py:2303-2306, 2995-3026): > 1 replaces the weight-normed
+    # conv by that many blocks Conv1d(k = max(3, conv_pos // depth)) -> LayerNorm(no affine) -> GELU
+    pos_conv_depth: int = 1
     # WavLM
     relative_position_embedding: bool = False
     num_buckets: int = 320
@@ -38,7 +41,13 @@ class ArchConfig:
 
     @property
     def family_id(self) -> int:
-        return {"hubert": 0, "wav2vec2": 1, "wavlm": 2, "distiller": 3}[self.family]
+        # data2vec's forward builds its frame mask the wav2vec 2.0 way (data2vec_model.py:455-476)
+        return {"hubert": 0, "wav2vec2": 1, "wavlm": 2, "distiller": 3, "data2vec": 1}[self.family]
+
+    @property
+    def pos_conv_kernel(self) -> int:
+        """Taps of one positional conv (wav2vec2_model.py:2996-2998)."""
+        return max(3, self.conv_pos // self.pos_conv_depth) if self.pos_conv_depth > 1 else self.conv_pos
 
     @property
     def num_outputs(self) -> int:
@@ -78,6 +87,12 @@ ARCHS: Dict[str, ArchConfig] = {
 ARCHS["distilhubert_base"] = ArchConfig(family="distiller", encoder_layers=2, feature_layer_norm=False, pred_heads=3)
 ARCHS["distilhubert"] = ARCHS["distilhubert_base"]
 
+# data2vec audio (s3prl/upstream/data2vec/hubconf.py:25-52; fairseq examples/data2vec base_librispeech / large_vox:
+# extractor_mode layer_norm, post-LN encoder, normalize, pos_conv_depth 5 with conv_pos 95 -> five k=19 blocks)
+_DATA2VEC = dict(family="data2vec", extractor_mode="layer_norm", normalize=True, conv_pos=95, pos_conv_depth=5)
+ARCHS["data2vec_base_960"] = replace(_BASE, **_DATA2VEC)
+ARCHS["data2vec_large_ll60k"] = replace(_BASE, **_DATA2VEC, **_LARGE)
+
 # Same-skeleton relatives: identical architecture, different pre-training data (only the checkpoint differs).
 for _alias, _arch in {
     # s3prl/upstream/wav2vec2/hubconf.py:123-160
@@ -100,6 +115,7 @@ ALIASES = {
     "wav2vec2_large": "wav2vec2_large_960",
     "wavlm": "wavlm_base",
     "unispeech_sat": "unispeech_sat_base_plus",
+    "data2vec": "data2vec_base_960",
 }
 
 
@@ -151,6 +167,7 @@ def arch_from_reference_cfg(family: str, model_cfg: dict, task_cfg: dict | None 
         encoder_attention_heads=int(g("encoder_attention_heads", 12)),
         conv_pos=int(g("conv_pos", 128)),
         conv_pos_groups=int(g("conv_pos_groups", 16)),
+        pos_conv_depth=int(g("pos_conv_depth", 1)),
         relative_position_embedding=bool(g("relative_position_embedding", False)),
         num_buckets=int(g("num_buckets", 320)),
         max_distance=int(g("max_distance", 800)),

@@ -45,6 +45,8 @@ def reference_model_cfg(cfg: ArchConfig) -> Dict:
         conv_pos_groups=cfg.conv_pos_groups,
         activation_fn="gelu",
     )
+    if cfg.pos_conv_depth > 1:
+        d.update(pos_conv_depth=cfg.pos_conv_depth)
     if cfg.family == "wavlm":
         d.update(
             normalize=cfg.normalize,
@@ -92,6 +94,8 @@ def converted_checkpoint(cfg: ArchConfig, state_dict: Mapping[str, torch.Tensor]
         "model_cfg": model_cfg,
         "model_weight": weights,
     }
+    if cfg.family == "data2vec":  # the reference deletes this key unconditionally (data2vec/convert.py:48-49)
+        out["model_weight"]["_ema"] = {}
     if cfg.family == "hubert":
         out["task_cfg"]["label_rate"] = 50.0
         out["model_cfg"]["label_rate"] = 50.0
@@ -171,7 +175,7 @@ _HF_LAYER = [
 def hf_to_fairseq_key(key: str, extractor_mode: str) -> Optional[str]:
     """fairseq name of a ``transformers`` Hubert/Wav2Vec2/WavLM *base model* parameter, or None for parameters the
     extraction forward does not use (masked_spec_embed, adapter / head weights)."""
-    key = re.sub(r"^(hubert|wav2vec2|wavlm)\.", "", key)
+    key = re.sub(r"^(hubert|wav2vec2|wavlm|data2vec_audio)\.", "", key)
     m = re.match(r"feature_extractor\.conv_layers\.(\d+)\.(conv|layer_norm)\.(weight|bias)$", key)
     if m:
         i, kind, wb = m.groups()
@@ -192,6 +196,9 @@ def hf_to_fairseq_key(key: str, extractor_mode: str) -> Optional[str]:
             "parametrizations.weight.original1": "weight_v",
         }.get(m.group(1))
         return None if tail is None else f"encoder.pos_conv.0.{tail}"
+    m = re.match(r"encoder\.pos_conv_embed\.layers\.(\d+)\.conv\.(weight|bias)$", key)
+    if m:  # Data2VecAudio: plain conv blocks (modeling_data2vec_audio.py Data2VecAudioPositionalConvLayer)
+        return f"encoder.pos_conv.{m.group(1)}.0.{m.group(2)}"
     m = re.match(r"encoder\.layer_norm\.(weight|bias)$", key)
     if m:
         return f"encoder.layer_norm.{m.group(1)}"
@@ -218,12 +225,30 @@ def hf_to_fairseq_state_dict(hf_state: Mapping[str, torch.Tensor], extractor_mod
 def arch_from_hf_config(hf_cfg) -> ArchConfig:
     """ArchConfig of a ``transformers`` HubertConfig / Wav2Vec2Config / WavLMConfig (base-model fields)."""
     model_type = getattr(hf_cfg, "model_type", "hubert")
-    family = {"hubert": "hubert", "wav2vec2": "wav2vec2", "wavlm": "wavlm", "unispeech-sat": "wavlm"}.get(model_type)
+    family = {"hubert": "hubert", "wav2vec2": "wav2vec2", "wavlm": "wavlm", "unispeech-sat": "wavlm",
+              "data2vec-audio": "data2vec"}.get(model_type)
     if family is None:
         raise ValueError(f"unsupported transformers model_type '{model_type}'")
     convs = list(zip(hf_cfg.conv_dim, hf_cfg.conv_kernel, hf_cfg.conv_stride))
     if [tuple(c) for c in convs] != CONV_LAYERS:
         raise ValueError(f"unsupported conv feature extractor: {convs}")
+    if family == "data2vec":
+        # Data2VecAudioConfig has neither feat_extract_norm nor do_stable_layer_norm: always "layer" + post-LN, and
+        # num_conv_pos_embeddings counts the conv blocks of conv_pos_kernel_size taps each
+        depth, k = int(hf_cfg.num_conv_pos_embeddings), int(hf_cfg.conv_pos_kernel_size)
+        return ArchConfig(
+            family="data2vec",
+            extractor_mode="layer_norm",
+            conv_bias=bool(hf_cfg.conv_bias),
+            normalize=True,
+            encoder_layers=hf_cfg.num_hidden_layers,
+            encoder_embed_dim=hf_cfg.hidden_size,
+            encoder_ffn_embed_dim=hf_cfg.intermediate_size,
+            encoder_attention_heads=hf_cfg.num_attention_heads,
+            conv_pos=depth * k,
+            conv_pos_groups=hf_cfg.num_conv_pos_embedding_groups,
+            pos_conv_depth=depth,
+        )
     return ArchConfig(
         family=family,
         extractor_mode="layer_norm" if hf_cfg.feat_extract_norm == "layer" else "default",

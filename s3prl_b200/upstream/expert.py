@@ -55,6 +55,7 @@ def _c_config(cfg: ArchConfig) -> _lib.S3BConfig:
     c.gru_rel_pos = int(cfg.gru_rel_pos)
     c.no_feature_layer_norm = int(not cfg.feature_layer_norm)
     c.pred_heads = int(cfg.pred_heads)
+    c.pos_conv_depth = int(cfg.pos_conv_depth)
     return c
 
 
@@ -363,7 +364,7 @@ def _family_of(name: str) -> str:
         return "wavlm"
     if name.startswith("distil"):
         return "distiller"
-    for fam in ("hubert", "wav2vec2", "wavlm"):
+    for fam in ("hubert", "wav2vec2", "wavlm", "data2vec"):
         if name.startswith(fam):
             return fam
     raise KeyError(f"cannot infer the model family from '{name}'")

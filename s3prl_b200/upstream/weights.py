@@ -46,12 +46,19 @@ def fabricate_state_dict(cfg: ArchConfig, seed: int = 0) -> Dict[str, torch.Tens
         sd["layer_norm.bias"] = randn(in_d, std=0.1)
     sd["post_extract_proj.weight"] = randn(D, in_d, std=1.0 / math.sqrt(in_d))
     sd["post_extract_proj.bias"] = randn(D, std=0.05)
-    # pos_conv with weight_norm(dim=2): g has one entry per kernel tap
     cpg = D // cfg.conv_pos_groups
-    v = randn(D, cpg, cfg.conv_pos, std=math.sqrt(4.0 / (cfg.conv_pos * D)))
-    sd["encoder.pos_conv.0.weight_v"] = v
-    sd["encoder.pos_conv.0.weight_g"] = v.norm(dim=(0, 1), keepdim=True) * randn(1, 1, cfg.conv_pos, std=0.1, mean=1.0)
-    sd["encoder.pos_conv.0.bias"] = randn(D, std=0.05)
+    if cfg.pos_conv_depth > 1:
+        # data2vec: plain Conv1d blocks (make_conv_block, wav2vec2_model.py:3000-3022; every block is followed by a LayerNorm, so the scale is immaterial)
+        k = cfg.pos_conv_kernel
+        for i in range(cfg.pos_conv_depth):
+            sd[f"encoder.pos_conv.{i}.0.weight"] = randn(D, cpg, k, std=1.0 / math.sqrt(cpg * k))
+            sd[f"encoder.pos_conv.{i}.0.bias"] = randn(D, std=0.05)
+    else:
+        # pos_conv with weight_norm(dim=2): g has one entry per kernel tap
+        v = randn(D, cpg, cfg.conv_pos, std=math.sqrt(4.0 / (cfg.conv_pos * D)))
+        sd["encoder.pos_conv.0.weight_v"] = v
+        sd["encoder.pos_conv.0.weight_g"] = v.norm(dim=(0, 1), keepdim=True) * randn(1, 1, cfg.conv_pos, std=0.1, mean=1.0)
+        sd["encoder.pos_conv.0.bias"] = randn(D, std=0.05)
     sd["encoder.layer_norm.weight"] = randn(D, std=0.1, mean=1.0)
     sd["encoder.layer_norm.bias"] = randn(D, std=0.1)
     for l in range(cfg.encoder_layers):
@@ -84,7 +91,7 @@ def fabricate_state_dict(cfg: ArchConfig, seed: int = 0) -> Dict[str, torch.Tens
 
 def load_reference_checkpoint(path: str, family: str) -> Tuple[ArchConfig, Dict[str, torch.Tensor]]:
     """Read a converted reference checkpoint: ``{"task_cfg","model_cfg","model_weight"[,"dictionaries_symbols"]}``
-    (s3prl/upstream/hubert/convert.py:37-56, wav2vec2/convert.py:26-39) or WavLM's ``{"cfg","model"}``
+    (s3prl/upstream/hubert/convert.py:37-56, wav2vec2/convert.py:26-39, data2vec/convert.py:31-52) or WavLM's ``{"cfg","model"}``
     (s3prl/upstream/wavlm/expert.py:37-40)."""
     state = torch.load(path, map_location="cpu", weights_only=False)
     if "model_weight" in state:
@@ -92,7 +99,10 @@ def load_reference_checkpoint(path: str, family: str) -> Tuple[ArchConfig, Dict[
             if key not in state:
                 raise ValueError(f"{path} is not a valid checkpoint since the required key: {key} is missing")
         cfg = arch_from_reference_cfg(family, dict(state["model_cfg"]), dict(state["task_cfg"]))
-        return cfg, state["model_weight"]
+        weights = state["model_weight"]
+        if family == "data2vec":  # the EMA teacher travels in the checkpoint and is dropped (data2vec/convert.py:48-49)
+            weights = {k: v for k, v in weights.items() if k != "_ema"}
+        return cfg, weights
     if "cfg" in state and "model" in state:
         return arch_from_reference_cfg("wavlm", dict(state["cfg"])), state["model"]
     if "Config" in state and "Distiller" in state:  # distiller/builder.py:41-47,129-131

@@ -138,7 +138,8 @@ def test_hub_covers_the_same_skeleton_relatives():
               "wav2vec2_large_960", "wav2vec2_large_ll60k", "wav2vec2_large_lv60_cv_swbd_fsh", "xlsr_53",
               "xls_r_300m", "wavlm_base", "wavlm_base_plus", "wavlm_large", "unispeech_sat_base",
               "unispeech_sat_base_plus", "unispeech_sat_large", "hubert_local", "wav2vec2_local", "wavlm_local",
-              "unispeech_sat_local", "distilhubert", "distilhubert_base", "distiller_local", "fbank", "mel", "linear"):
+              "unispeech_sat_local", "distilhubert", "distilhubert_base", "distiller_local", "data2vec", "data2vec_base_960",
+              "data2vec_large_ll60k", "data2vec_local", "fbank", "mel", "linear"):
         assert n in names, n
     for n in ("xls_r_1b", "xls_r_2b", "wav2vec2_conformer_relpos"):
         assert n not in names
@@ -148,6 +149,10 @@ def test_hub_covers_the_same_skeleton_relatives():
     ul = get_arch("unispeech_sat_large")
     assert ul.layer_norm_first and ul.extractor_mode == "layer_norm" and ul.encoder_layers == 24
     assert get_arch("unispeech_sat") == u
+    d = get_arch("data2vec")  # five k = 19 conv blocks instead of the weight-normed k = 128 conv (data2vec/hubconf.py:25-52)
+    assert d.family == "data2vec" and d.family_id == 1 and d.pos_conv_depth == 5 and d.pos_conv_kernel == 19
+    assert d.extractor_mode == "layer_norm" and d.normalize and not d.layer_norm_first
+    assert get_arch("data2vec_large_ll60k").encoder_layers == 24
 
 
 def _gloo_worker(rank, world, port, tmpdir):
@@ -204,7 +209,7 @@ def test_converted_checkpoint_layouts_roundtrip(tmp_path):
     from s3prl_b200.upstream.weights import fabricate_state_dict, load_reference_checkpoint
 
     for name in ("hubert_base", "wav2vec2_large_ll60k", "wavlm_base_plus", "unispeech_sat_base_plus", "wavlm_large",
-                 "distilhubert_base"):
+                 "distilhubert_base", "data2vec_base_960"):
         cfg = ARCHS[name]
         sd = fabricate_state_dict(cfg, 0)
         path = tmp_path / f"{name}.pt"
@@ -214,7 +219,7 @@ def test_converted_checkpoint_layouts_roundtrip(tmp_path):
         assert got_sd.keys() == sd.keys() and all(torch.equal(got_sd[k], sd[k]) for k in sd)
         # the hub's *_local entry builds an expert from the file (no GPU needed until the first forward)
         local = {"hubert": "hubert_local", "wav2vec2": "wav2vec2_local", "wavlm": "wavlm_local",
-                 "distiller": "distiller_local"}[cfg.family]
+                 "distiller": "distiller_local", "data2vec": "data2vec_local"}[cfg.family]
         e = hub.ENTRIES[local](str(path))
         assert e.arch == cfg and e.num_layers == cfg.encoder_layers
     layout = converted_checkpoint(ARCHS["hubert_base"], {})
@@ -257,6 +262,7 @@ def test_fairseq_state_conversion():
     ("hubert", dict(feat_extract_norm="layer", do_stable_layer_norm=True, conv_bias=True)),
     ("wav2vec2", {}),
     ("wavlm", {}),
+    ("data2vec", {}),
 ])
 def test_huggingface_second_oracle(kind, kw):
     """N4: the HF -> fairseq parameter-name map (upstream/convert.py) against an INDEPENDENT implementation: a random
@@ -271,8 +277,10 @@ def test_huggingface_second_oracle(kind, kw):
     import upstream_oracle as O
     from s3prl_b200.upstream.convert import hf_to_fairseq_key, load_hf_model
 
-    Cfg = {"hubert": transformers.HubertConfig, "wav2vec2": transformers.Wav2Vec2Config, "wavlm": transformers.WavLMConfig}[kind]
-    Mod = {"hubert": transformers.HubertModel, "wav2vec2": transformers.Wav2Vec2Model, "wavlm": transformers.WavLMModel}[kind]
+    Cfg = {"hubert": transformers.HubertConfig, "wav2vec2": transformers.Wav2Vec2Config, "wavlm": transformers.WavLMConfig,
+           "data2vec": transformers.Data2VecAudioConfig}[kind]
+    Mod = {"hubert": transformers.HubertModel, "wav2vec2": transformers.Wav2Vec2Model, "wavlm": transformers.WavLMModel,
+           "data2vec": transformers.Data2VecAudioModel}[kind]
     torch.manual_seed(0)
     cfg = Cfg(num_hidden_layers=2, **kw)
     cfg.layerdrop = 0.0

@@ -16,7 +16,7 @@ from s3prl_b200.upstream.weights import fabricate_state_dict  # noqa: E402
 
 MODEL_FIXTURES = sorted(p.stem for p in GOLDEN.glob("*.pt") if p.stem in ARCHS)
 # full-size 24-layer models take a while on CPU; the fast subset keeps the default CPU suite to a few minutes
-FAST = {"hubert_base", "wavlm_base_plus", "wav2vec2_base_960", "unispeech_sat_base_plus"}
+FAST = {"hubert_base", "wavlm_base_plus", "wav2vec2_base_960", "unispeech_sat_base_plus", "data2vec_base_960"}
 
 
 def _wavs(lens, seed):

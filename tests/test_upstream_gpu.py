@@ -87,6 +87,8 @@ def test_matches_reference_golden(s3b_lib, name):
         ("wav2vec2_base_960", [16000, 50, 399, 5]),  # shorter than the receptive field: the reference's mask index wraps
         ("wavlm_base_plus", [40000, 33333, 900]),
         ("distilhubert_base", [40000, 33333, 900]),  # feat_final + 2 layer outputs + 3 prediction heads
+        ("data2vec_base_960", [40000, 33333, 900]),  # five conv blocks as positional encoder, nothing re-masked between
+        ("data2vec_base_960", [16000, 50, 399]),     # them; wav2vec 2.0 mask rule incl. the wrap-around of short inputs
     ],
 )
 def test_matches_oracle_ragged(s3b_lib, name, lens):
@@ -109,6 +111,33 @@ def test_matches_oracle_ragged(s3b_lib, name, lens):
     valid = expert.valid_frames(lens)
     assert valid == O.valid_frames(cfg.family, lens, max(lens))
     print(f"{name} lens={lens}: worst per-layer relative error vs oracle = {worst:.3e}")
+
+
+@pytest.mark.parametrize("depth,conv_pos,dim", [(2, 95, 768), (4, 96, 768), (5, 95, 1024), (3, 9, 768)])
+def test_positional_conv_block_variants(s3b_lib, depth, conv_pos, dim):
+    """pos_conv_depth > 1 (make_conv_block, wav2vec2_model.py:2995-3026) beyond the published data2vec shape: k = 47
+    (rounded up to 48 taps), an EVEN k = 24 (SamePad drops the last frame), 64 channels per group, and the k = 3 floor
+    of max(3, conv_pos // depth); two-layer encoders against the oracle, ragged batch."""
+    import dataclasses
+
+    import upstream_oracle as O
+    from s3prl_b200.upstream.configs import ARCHS
+    from s3prl_b200.upstream.expert import UpstreamExpert
+    from s3prl_b200.upstream.weights import fabricate_state_dict
+
+    cfg = dataclasses.replace(ARCHS["data2vec_base_960"], encoder_layers=2, pos_conv_depth=depth, conv_pos=conv_pos,
+                              encoder_embed_dim=dim, encoder_attention_heads=dim // 64, encoder_ffn_embed_dim=4 * dim)
+    sd = fabricate_state_dict(cfg, seed=3)
+    lens = [24000, 17777, 1000]
+    wavs = _wavs(lens, seed=77)
+    with torch.no_grad():
+        ref, _pad = O.upstream_forward(wavs, sd, cfg)
+    _EXPERTS.clear()
+    expert = UpstreamExpert(arch=cfg, state_dict=sd, name="data2vec_variant").to("cuda")
+    hs = expert([w.cuda() for w in wavs])["hidden_states"]
+    assert len(hs) == len(ref) == 3
+    for l, (h, r) in enumerate(zip(hs, ref)):
+        _compare(h.cpu(), r, f"pos_conv depth={depth} conv_pos={conv_pos} D={dim} layer {l}")
 
 
 def test_forward_host_matches_device(s3b_lib):
@@ -232,7 +261,7 @@ def test_local_checkpoint_entries(s3b_lib, tmp_path):
     wavs = [w.cuda() for w in _wavs([12000, 7001], seed=3)]
     for name, local in (("hubert_base", "hubert_local"), ("wav2vec2_base_960", "wav2vec2_local"),
                         ("wavlm_base_plus", "wavlm_local"), ("unispeech_sat_base_plus", "unispeech_sat_local"),
-                        ("distilhubert_base", "distiller_local")):
+                        ("distilhubert_base", "distiller_local"), ("data2vec_base_960", "data2vec_local")):
         path = tmp_path / f"{name}.pt"
         save_converted_checkpoint(path, ARCHS[name], fabricate_state_dict(ARCHS[name], 0))
         _EXPERTS.clear()
