@@ -496,7 +496,12 @@ def run_ours(args):
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
     flops_utt, _ = algorithmic_flops_per_utt(cfg, L)
-    lanes_used = int(os.environ.get("S3B_LANES", "2")) if args.lanes is None else args.lanes
+    if args.lanes is None:  # the library's choice for this shard (two lanes from a measured frame count on)
+        from s3prl_b200 import lib as _s3b_lib
+
+        lanes_used = int(_s3b_lib.load().s3b_default_lanes(None, len(my_ids), L))
+    else:
+        lanes_used = args.lanes
     scheme = os.environ.get("S3B_GEMM_SCHEME", "f16q8")  # the library's default (model.cu S3B_DEFAULT_SCHEME)
     if scheme in ("1", "f16q8"):
         scheme, slots = "f16q8", 2.0

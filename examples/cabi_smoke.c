@@ -25,7 +25,7 @@ int main(void) {
         (const void*)s3b_forward_host_ex, (const void*)s3b_wavlm_buckets, (const void*)s3b_peer_create,
         (const void*)s3b_peer_connect,   (const void*)s3b_peer_slot,       (const void*)s3b_peer_push,
         (const void*)s3b_peer_wait,      (const void*)s3b_peer_destroy,    (const void*)s3b_gemm_bench,
-        (const void*)s3b_num_outputs,
+        (const void*)s3b_num_outputs,    (const void*)s3b_default_lanes,
     };
     s3b_config cfg;
     int64_t lens[2] = {16000, 800};

@@ -114,6 +114,9 @@ typedef struct s3b_forward_opts {
 } s3b_forward_opts;
 int s3b_forward_ex(s3b_model* m, const float* const* wavs, const int64_t* lens, int32_t batch, int64_t max_len,
                    float* hidden_out, void* stream, const s3b_forward_opts* opts);
+/* Lanes the library picks for a batch when opts->lanes == 0 (two from a measured frame count on, else one;
+ * S3B_LANES / S3B_LANE_MIN_FRAMES override). No reference counterpart: scheduling only, results are bit-identical. */
+int32_t s3b_default_lanes(const s3b_model* m, int32_t batch, int64_t max_len);
 /* s3b_forward_host that also leaves the hidden states in a caller-owned DEVICE buffer [NL+1][batch][T][D]
  * (hidden_out_dev may be NULL = internal staging), so that a device-side consumer (Featurizer, all-gather) can run
  * without re-uploading them. */

@@ -121,6 +121,10 @@ struct SplitBuf {
 #ifndef S3B_DEFAULT_SCHEME
 #define S3B_DEFAULT_SCHEME 1
 #endif
+// Frames (batch x T) from which a forward call is split into two utterance lanes (default_lanes below)
+#ifndef S3B_LANE_MIN_FRAMES_DEFAULT
+#define S3B_LANE_MIN_FRAMES_DEFAULT 12000
+#endif
 
 static const int kNumConv = 7;
 static const int kConvK[kNumConv] = {10, 3, 3, 3, 3, 2, 2};
@@ -1453,17 +1457,29 @@ int Fwd::stage(int s) {
     return 0;
 }
 
-// Number of lanes for a batch: S3B_LANES overrides; otherwise two lanes whenever the batch can be split.
-static int default_lanes(int B) {
+// Number of lanes for a batch: S3B_LANES overrides; otherwise two lanes when the batch can be split AND carries at
+// least kLaneMinFrames frames (S3B_LANE_MIN_FRAMES overrides). Below that the halves no longer fill the SMs and the
+// doubled launch count costs more than the overlap wins. Same-box pairs, hubert_base 10 s utterances, one lane vs two:
+// 4 per rank (2 k frames, the 8-GPU shard of BASELINE C2) 2.40 / 2.56 ms, 8 (4 k) 3.98 / 4.00, 16 (8 k) 7.06 / 7.13,
+// 32 (16 k) 13.31 / 13.07 (profiles/README.md r2a, r2p, r2q).
+static constexpr int64_t kLaneMinFrames = S3B_LANE_MIN_FRAMES_DEFAULT;
+static int default_lanes(int B, int64_t T) {
     static int env = -2;
+    static long long min_frames = -1;
     if (env == -2) {
         const char* e = getenv("S3B_LANES");
         env = e ? atoi(e) : -1;
+        const char* f = getenv("S3B_LANE_MIN_FRAMES");
+        min_frames = f ? atoll(f) : (long long)kLaneMinFrames;
     }
-    int lanes = env > 0 ? env : 2;
-    if (lanes > 2) lanes = 2;
-    if (B < 2) lanes = 1;
-    return lanes;
+    if (B < 2) return 1;
+    if (env > 0) return env > 2 ? 2 : env;
+    return (long long)B * T >= min_frames ? 2 : 1;
+}
+
+extern "C" int32_t s3b_default_lanes(const s3b_model*, int32_t batch, int64_t max_len) {
+    const int64_t T = num_frames(max_len);
+    return (batch < 1 || T < 1) ? -1 : default_lanes(batch, T);
 }
 
 static int forward_lanes(s3b_model* m, const float* const* wavs, const int64_t* lens, int B, int64_t Lmax,
@@ -1472,7 +1488,7 @@ static int forward_lanes(s3b_model* m, const float* const* wavs, const int64_t* 
     if (B < 1) return fail("empty batch");
     const int64_t T = num_frames(Lmax);
     if (T < 1) return fail("max_len %lld too short: the conv stack yields no frame", (long long)Lmax);
-    int lanes = (o && o->lanes > 0) ? o->lanes : default_lanes(B);
+    int lanes = (o && o->lanes > 0) ? o->lanes : default_lanes(B, T);
     if (lanes > 2) lanes = 2;
     if (lanes > B) lanes = B;
     const size_t frame = (size_t)T * c.embed_dim;

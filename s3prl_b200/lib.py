@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = [
     "s3b_num_frames",
     "s3b_valid_frames",
     "s3b_num_outputs",
+    "s3b_default_lanes",
     "s3b_forward",
     "s3b_forward_host",
     "s3b_forward_ex",
@@ -134,6 +135,8 @@ def load() -> C.CDLL:
     lib.s3b_num_frames.restype = i64
     lib.s3b_num_outputs.argtypes = [vp]
     lib.s3b_num_outputs.restype = i32
+    lib.s3b_default_lanes.argtypes = [vp, i32, i64]
+    lib.s3b_default_lanes.restype = i32
     lib.s3b_valid_frames.argtypes = [vp, C.POINTER(i64), i32, i64, C.POINTER(i32)]
     lib.s3b_forward.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i32, i64, f32p, vp]
     lib.s3b_forward_host.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i32, i64, f32p]

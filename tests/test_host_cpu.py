@@ -40,6 +40,18 @@ def test_no_cpu_fallback(s3b_lib):
         fbank()([torch.randn(16000)])
 
 
+def test_default_lanes_rule(s3b_lib):
+    """Scheduling only (results are bit-identical, tests/test_upstream_gpu.py::test_lanes_are_bit_identical): two
+    utterance lanes from 12 k frames per call on, one below — the measured crossover (profiles/README.md r2p / r2q)."""
+    if os.environ.get("S3B_LANES") or os.environ.get("S3B_LANE_MIN_FRAMES"):
+        pytest.skip("lane override set in the environment")
+    f = s3b_lib.s3b_default_lanes
+    assert f(None, 32, 160000) == 2 and f(None, 16, 320000) == 2   # BASELINE C2 / C3 on one GPU
+    assert f(None, 16, 160000) == 1 and f(None, 8, 160000) == 1 and f(None, 4, 160000) == 1  # their 2 / 4 / 8-GPU shards
+    assert f(None, 1, 16000000) == 1  # a single utterance cannot be split
+    assert f(None, 0, 160000) == -1 and f(None, 4, 100) == -1
+
+
 def test_config_from_reference_cfg_dict():
     from s3prl_b200.upstream.configs import ARCHS, arch_from_reference_cfg
 
