@@ -40,6 +40,41 @@ def test_no_cpu_fallback(s3b_lib):
         fbank()([torch.randn(16000)])
 
 
+def test_model_create_validates_the_architecture(s3b_lib):
+    """s3b_model_create needs no device: unsupported shapes are refused with a message instead of failing later."""
+    import ctypes as C
+
+    from s3prl_b200 import lib
+    from s3prl_b200.upstream.configs import ARCHS
+    from s3prl_b200.upstream.expert import _c_config
+
+    def create(cfg, **over):
+        c = _c_config(cfg)
+        for k, v in over.items():
+            setattr(c, k, v)
+        h = C.c_void_p()
+        rc = s3b_lib.s3b_model_create(C.byref(c), C.byref(h))
+        if rc == 0:
+            s3b_lib.s3b_model_destroy(h)
+        return rc, s3b_lib.s3b_last_error().decode()
+
+    for name in ("hubert_base", "wav2vec2_large_ll60k", "wavlm_large", "distilhubert_base", "data2vec_base_960",
+                 "data2vec_large_ll60k"):
+        assert create(ARCHS[name])[0] == 0, name
+    rc, msg = create(ARCHS["hubert_base"], num_heads=16)  # 48-wide heads
+    assert rc != 0 and "head dim" in msg
+    rc, msg = create(ARCHS["data2vec_base_960"], family=lib.FAMILY_HUBERT)  # conv blocks go with the wav2vec2 mask rule
+    assert rc != 0 and "pos_conv_depth" in msg
+    rc, msg = create(ARCHS["data2vec_base_960"], pos_conv_depth=9)
+    assert rc != 0 and "pos_conv_depth" in msg
+    rc, msg = create(ARCHS["hubert_base"], pos_conv_kernel=127)  # the weight-normed conv needs an even kernel here
+    assert rc != 0 and "even" in msg
+    rc, msg = create(ARCHS["hubert_base"], pred_heads=3)  # prediction heads without the distiller front end: fine
+    assert rc == 0
+    rc, msg = create(ARCHS["hubert_base"], no_feature_layer_norm=1)
+    assert rc != 0 and "distiller" in msg
+
+
 def test_default_lanes_rule(s3b_lib):
     """Scheduling only (results are bit-identical, tests/test_upstream_gpu.py::test_lanes_are_bit_identical): two
     utterance lanes from 12 k frames per call on, one below — the measured crossover (profiles/README.md r2p / r2q)."""
