@@ -1,1 +1,1 @@
-from .upstream import S3PRLUpstream  # noqa: F401
+from .upstream import Featurizer, S3PRLUpstream, UpstreamDownstreamModel  # noqa: F401

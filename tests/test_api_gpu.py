@@ -59,6 +59,55 @@ def test_s3prl_upstream_wrapper(s3b_lib):
     assert torch.equal(all_hs[3][:, 49], all_hs[3][:, 48])
 
 
+def test_nn_featurizer_and_model_wrapper(s3b_lib):
+    """s3prl.nn.Featurizer / UpstreamDownstreamModel mirrors (s3prl/nn/upstream.py:234-384) on the device: DistilHuBERT's
+    six outputs through S3PRLUpstream, layer selection + normalize through the fused weighted sum, weight gradient vs
+    the torch formulation. (The host logic is compared with the reference's own classes in tests/test_host_cpu.py.)"""
+    import torch.nn.functional as F
+
+    from s3prl_b200.nn import Featurizer, S3PRLUpstream, UpstreamDownstreamModel
+
+    model = S3PRLUpstream("distilhubert_base").to("cuda")
+    assert model.num_layers == 6
+    lens = torch.tensor([16000, 9000, 3200])
+    wavs = torch.zeros(3, 16000)
+    g = torch.Generator().manual_seed(9)
+    for i, n in enumerate(lens.tolist()):
+        wavs[i, :n] = torch.randn(n, generator=g)
+    all_hs, all_lens = model(wavs.cuda(), lens.cuda())
+    assert len(all_hs) == 6 and all_hs[0].shape == (3, 50, 768) and all_lens[0].tolist() == [50, 29, 10]
+    for sel, norm in ((None, False), ([5, 0, 2], True)):
+        feat = Featurizer(model, sel, norm).to("cuda")
+        with torch.no_grad():
+            feat.weights.copy_(torch.randn(len(feat.weights), generator=g).cuda())
+        hs, hs_len = feat(all_hs, all_lens)
+        picked = [all_hs[i] for i in feat.layer_selections]
+        if norm:
+            picked = [F.layer_norm(h, (768,)) for h in picked]
+        w = feat.weights.detach().clone().requires_grad_(True)
+        ref = (torch.softmax(w, -1).view(-1, 1, 1, 1) * torch.stack(picked, 0)).sum(0)
+        assert hs.shape == (3, 50, 768) and torch.equal(hs_len, all_lens[0])
+        assert torch.allclose(hs, ref, atol=1e-5, rtol=1e-5)
+        hs.square().sum().backward()
+        ref.square().sum().backward()
+        assert torch.allclose(feat.weights.grad, w.grad, rtol=2e-3, atol=1e-3 * w.grad.abs().max().item())
+
+    class Head(torch.nn.Module):
+        output_size = 8
+
+        def __init__(self):
+            super().__init__()
+            self.proj = torch.nn.Linear(768, 8)
+
+        def forward(self, h, h_len):
+            return self.proj(h), h_len
+
+    full = UpstreamDownstreamModel(model, Featurizer(model).to("cuda"), Head().cuda())
+    out, out_len = full(wavs.cuda(), lens.cuda())
+    assert out.shape == (3, 50, 8) and out_len.tolist() == [50, 29, 10] and out.requires_grad
+    assert full.downsample_rate == 320 and full.output_size == 8
+
+
 def test_frozen_upstream_ctc_training_steps(s3b_lib):
     """The SUPERB recipe of BASELINE config 5 in miniature (s3prl/downstream/runner.py:293-330, ctc/expert.py:64-108):
     frozen upstream under no_grad, trainable Featurizer weights + a linear CTC head, synthetic LibriSpeech-shaped

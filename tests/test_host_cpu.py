@@ -347,6 +347,83 @@ def test_huggingface_second_oracle(kind, kw):
         assert ((a - b).norm() / b.norm()).item() < 5e-6
 
 
+@pytest.mark.skipif(not (REFERENCE / "s3prl" / "nn" / "upstream.py").exists() and not (ROOT / "oracle" / "_ref" / "s3prl").exists(),
+                    reason="needs the reference (s3prl.nn) to compare against")
+def test_nn_featurizer_matches_reference_logic(monkeypatch):
+    """s3prl_b200.nn.Featurizer / UpstreamDownstreamModel against the reference's own classes (s3prl/nn/upstream.py:234-384)
+    on the CPU: layer selection, normalize, single-layer pass-through, weights and their gradient. The fused CUDA sum is
+    replaced by its torch definition for this host-logic test (the kernel itself is pinned in tests/test_api_gpu.py)."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import ref_runtime
+
+    ref_runtime.activate()
+    from s3prl.nn.upstream import Featurizer as RefFeaturizer
+    from s3prl.nn.upstream import UpstreamDownstreamModel as RefUDM
+
+    import s3prl_b200.upstream.featurizer as fused
+    from s3prl_b200.nn import Featurizer, UpstreamDownstreamModel
+
+    def torch_sum(feature, norm_weights):
+        return (norm_weights.view(-1, 1, 1, 1) * torch.stack(list(feature), 0)).sum(0)
+
+    with pytest.raises(fused._lib.S3BError):  # the product path has no CPU fallback
+        fused.weighted_sum([torch.zeros(1, 4, 8)] * 2, torch.ones(2) / 2)
+    monkeypatch.setattr(fused, "weighted_sum", torch_sum)
+
+    class FakeUpstream:
+        def __init__(self, n):
+            self.num_layers, self.hidden_sizes, self.downsample_rates = n, [16] * n, [320] * n
+
+    g = torch.Generator().manual_seed(0)
+    hs = [torch.randn(3, 7, 16, generator=g) for _ in range(5)]
+    lens = [torch.tensor([7, 5, 2])] * 5
+    for sel, norm in ((None, False), ([4, 0, 2], False), (None, True), ([1, 3], True)):
+        ours, ref = Featurizer(FakeUpstream(5), sel, norm), RefFeaturizer(FakeUpstream(5), sel, norm)
+        w = torch.randn(len(ours.weights), generator=g)
+        with torch.no_grad():
+            ours.weights.copy_(w), ref.weights.copy_(w)
+        assert ours.layer_selections == ref.layer_selections
+        (a, al), (b, bl) = ours(hs, lens), ref(hs, lens)
+        assert torch.allclose(a, b, atol=1e-6) and torch.equal(al, bl)
+        a.square().sum().backward(), b.square().sum().backward()
+        assert torch.allclose(ours.weights.grad, ref.weights.grad, rtol=1e-5, atol=1e-6)
+        assert ours.output_size == ref.output_size == 16 and ours.downsample_rate == ref.downsample_rate == 320
+    one, one_ref = Featurizer(FakeUpstream(1)), RefFeaturizer(FakeUpstream(1))
+    assert not hasattr(one, "weights") and not hasattr(one_ref, "weights")
+    assert one(hs[:1], lens[:1])[0] is hs[0]
+
+    class Up(torch.nn.Module):
+        num_layers, hidden_sizes, downsample_rates = 5, [16] * 5, [320] * 5
+
+        def forward(self, wav, wav_len):
+            return hs, lens
+
+    class Down(torch.nn.Module):
+        output_size = 3
+
+        def forward(self, h, h_len, scale=1.0):
+            return h.mean(-1) * scale, h_len
+
+    f = Featurizer(Up())
+    ours, ref = UpstreamDownstreamModel(Up(), f, Down()), RefUDM(Up(), f, Down())
+    (a, al), (b, bl) = ours(None, None, scale=2.0), ref(None, None, scale=2.0)
+    assert torch.equal(a, b) and torch.equal(al, bl)
+    assert (ours.input_size, ours.downsample_rate, ours.output_size) == (ref.input_size, ref.downsample_rate, ref.output_size)
+    with pytest.raises(NotImplementedError):
+        UpstreamDownstreamModel(Up(), f, Down(), upstream_trainable=True)
+
+
+def test_s3prl_upstream_wrapper_layer_counts():
+    """S3PRLUpstream's static facts without a device: NL + 1 entries for the encoders, feat_final + layers + prediction
+    heads for DistilHuBERT (s3prl/upstream/distiller/expert.py:44-63), one for fbank."""
+    from s3prl_b200.nn import S3PRLUpstream
+
+    assert S3PRLUpstream("hubert_base").num_layers == 13
+    assert S3PRLUpstream("data2vec_large_ll60k").num_layers == 25
+    d = S3PRLUpstream("distilhubert_base")
+    assert d.num_layers == 6 and d.hidden_sizes == [768] * 6 and d.downsample_rates == [320] * 6
+
+
 def _reference_install():
     for cand in (REFERENCE, ROOT / "oracle" / "_ref"):
         if (cand / "s3prl" / "downstream" / "runner.py").exists():
