@@ -29,12 +29,22 @@ def _make_entry(name: str) -> Callable:
     return entry
 
 
-def _make_local_entry(family: str) -> Callable:
+def _make_local_entry(family: str, suffix: str = "local") -> Callable:
+    """``*_local`` / ``*_custom`` / ``*_url`` (hubert/hubconf.py:57-78 and its siblings): in the reference the latter two
+    download ``ckpt`` when it is a URL and then behave like ``*_local``; there is no network here, so a URL is refused
+    with a message and a path is read as the converted checkpoint it must be."""
+
     def entry(ckpt, *args, **kwargs):
         assert isinstance(ckpt, str), "a converted checkpoint path is required"
+        if ckpt.startswith("http"):
+            raise ValueError(f"{family}_{suffix}: remote checkpoints are not reachable here; download {ckpt} and pass the file")
+        kwargs.pop("refresh", None)
+        if kwargs.pop("legacy", False):  # hubert_custom(legacy=True): un-converted fairseq file, needs fairseq itself
+            raise ValueError(f"{family}_{suffix}: legacy fairseq checkpoints are not supported; convert first "
+                             "(s3prl_b200.upstream.convert.convert_fairseq_checkpoint)")
         return UpstreamExpert(ckpt=ckpt, name=f"{family}_local", **kwargs)
 
-    entry.__name__ = f"{family}_local"
+    entry.__name__ = f"{family}_{suffix}"
     return entry
 
 
@@ -43,6 +53,9 @@ for _name in list(ARCHS) + list(ALIASES):
     ENTRIES[_name] = _make_entry(_name)
 for _family in ("hubert", "wav2vec2", "wavlm", "unispeech_sat", "distiller", "data2vec"):
     ENTRIES[f"{_family}_local"] = _make_local_entry(_family)
+    ENTRIES[f"{_family}_url"] = _make_local_entry(_family, "url")
+for _family in ("hubert", "wav2vec2", "data2vec"):  # the families whose hubconf defines *_custom
+    ENTRIES[f"{_family}_custom"] = _make_local_entry(_family, "custom")
 globals().update(ENTRIES)
 
 

@@ -186,7 +186,8 @@ def test_hub_covers_the_same_skeleton_relatives():
               "xls_r_300m", "wavlm_base", "wavlm_base_plus", "wavlm_large", "unispeech_sat_base",
               "unispeech_sat_base_plus", "unispeech_sat_large", "hubert_local", "wav2vec2_local", "wavlm_local",
               "unispeech_sat_local", "distilhubert", "distilhubert_base", "distiller_local", "data2vec", "data2vec_base_960",
-              "data2vec_large_ll60k", "data2vec_local", "fbank", "mel", "linear"):
+              "data2vec_large_ll60k", "data2vec_local", "hubert_custom", "hubert_url", "wav2vec2_custom", "wav2vec2_url",
+              "wavlm_url", "unispeech_sat_url", "distiller_url", "data2vec_custom", "data2vec_url", "fbank", "mel", "linear"):
         assert n in names, n
     for n in ("xls_r_1b", "xls_r_2b", "wav2vec2_conformer_relpos"):
         assert n not in names
@@ -269,6 +270,12 @@ def test_converted_checkpoint_layouts_roundtrip(tmp_path):
                  "distiller": "distiller_local", "data2vec": "data2vec_local"}[cfg.family]
         e = hub.ENTRIES[local](str(path))
         assert e.arch == cfg and e.num_layers == cfg.encoder_layers
+        url_entry = hub.ENTRIES[local.replace("_local", "_url")]  # *_url / *_custom: a path works, a URL is refused
+        assert url_entry(str(path), refresh=True).arch == cfg
+        with pytest.raises(ValueError, match="not reachable"):
+            url_entry("https://huggingface.co/s3prl/converted_ckpts/resolve/main/x.pt")
+    with pytest.raises(ValueError, match="legacy"):
+        hub.ENTRIES["hubert_custom"](str(tmp_path / "hubert_base.pt"), legacy=True)
     layout = converted_checkpoint(ARCHS["hubert_base"], {})
     assert set(layout) == {"task_cfg", "model_cfg", "model_weight", "dictionaries_symbols"}
     assert set(converted_checkpoint(ARCHS["wav2vec2_base_960"], {})) == {"task_cfg", "model_cfg", "model_weight"}
