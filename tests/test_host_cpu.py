@@ -420,6 +420,59 @@ def test_nn_featurizer_matches_reference_logic(monkeypatch):
         UpstreamDownstreamModel(Up(), f, Down(), upstream_trainable=True)
 
 
+def _fake_wrapped(cls, ours: bool):
+    """An S3PRLUpstream (ours or the reference's) around a fake three-layer upstream with the conv stack's frame rule."""
+
+    class Fake(torch.nn.Module):
+        def forward(self, wavs):
+            frames = max((len(w) - 400) // 320 + 1 if len(w) >= 400 else 0 for w in wavs)
+            base = torch.arange(len(wavs) * frames * 2, dtype=torch.float32).view(len(wavs), frames, 2)
+            return {"hidden_states": [base + k for k in range(3)]}
+
+    obj = cls.__new__(cls)
+    torch.nn.Module.__init__(obj)
+    obj.upstream, obj.normalize = Fake(), False
+    obj._hidden_sizes, obj._downsample_rates = [2] * 3, [320] * 3
+    if not ours:
+        obj._num_layers = 3
+    return obj
+
+
+@pytest.mark.skipif(not (REFERENCE / "s3prl" / "nn" / "upstream.py").exists() and not (ROOT / "oracle" / "_ref" / "s3prl").exists(),
+                    reason="needs the reference (s3prl.nn) to compare against")
+def test_s3prl_upstream_bookkeeping_matches_reference_class():
+    """The length bookkeeping of s3prl_b200.nn.S3PRLUpstream.forward (frame count per layer, last-frame repeat / cut,
+    h_len, the 0.05 s minimum, normalize) next to the reference's own class (s3prl/nn/upstream.py:166-231) on the same
+    fake upstream: identical tensors, and the same AssertionError where the reference refuses a 2x frame mismatch."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import ref_runtime
+
+    ref_runtime.activate()
+    from s3prl.nn.upstream import S3PRLUpstream as Ref
+
+    from s3prl_b200.nn import S3PRLUpstream as Ours
+
+    ref, ours = _fake_wrapped(Ref, False), _fake_wrapped(Ours, True)
+    g = torch.Generator().manual_seed(0)
+    for lens in ([16000, 9000, 3200], [16001, 480], [700, 500], [32000, 31999], [1281, 1280, 1279], [48000]):
+        for normalize in (False, True):
+            ref.normalize = ours.normalize = normalize
+            width = max(lens) + 37  # the padded tensor may be wider than the longest utterance
+            wavs = torch.zeros(len(lens), width)
+            for i, n in enumerate(lens):
+                wavs[i, :n] = torch.randn(n, generator=g)
+            for w in (wavs, wavs.unsqueeze(-1)):
+                (a_hs, a_len), (b_hs, b_len) = ref(w, torch.tensor(lens)), ours(w, torch.tensor(lens))
+                assert len(a_hs) == len(b_hs) == 3
+                assert all(torch.equal(x, y) for x, y in zip(a_hs, b_hs)), lens
+                assert all(torch.equal(x, y) for x, y in zip(a_len, b_len)), lens
+    for lens in ([960, 961], [1000, 900]):  # 2 frames from the conv rule where ceil(L / 320) = 4: refused by both
+        wavs = torch.zeros(len(lens), max(lens))
+        for cls_obj in (ref, ours):
+            with pytest.raises(AssertionError):
+                cls_obj(wavs, torch.tensor(lens))
+
+
 def test_s3prl_upstream_wrapper_layer_counts():
     """S3PRLUpstream's static facts without a device: NL + 1 entries for the encoders, feat_final + layers + prediction
     heads for DistilHuBERT (s3prl/upstream/distiller/expert.py:44-63), one for fbank."""
